@@ -1,0 +1,374 @@
+// extern "C" entry points of libpicard_b200.so (include/picard_b200.h).  Every call is wrapped so that C++
+// exceptions become PicardError-shaped status codes (error.rs:9-42) with the Display text in `err`.
+#include <cstdarg>
+
+#include "engine.cuh"
+#include "jade.cuh"
+
+using namespace picard;
+
+namespace {
+void set_err(char* err, size_t errlen, const std::string& msg) {
+  if (err && errlen) snprintf(err, errlen, "%s", msg.c_str());
+}
+template <typename F>
+int guarded(char* err, size_t errlen, F&& f) {
+  try {
+    if (err && errlen) err[0] = 0;
+    f();
+    return PICARD_OK;
+  } catch (const Error& e) {
+    set_err(err, errlen, e.what());
+    return e.status;
+  } catch (const std::bad_alloc&) {
+    set_err(err, errlen, "Computation error: out of host memory");
+    return PICARD_COMPUTATION_ERROR;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, std::string("Computation error: ") + e.what());
+    return PICARD_COMPUTATION_ERROR;
+  }
+}
+// Host (n x t, row_stride) -> fresh device buffer with an even, 16-aligned leading dimension.
+struct Staged {
+  DevBuf<double> buf;
+  int64_t ld = 0;
+  Staged(const double* x, int64_t n, int64_t t, int64_t row_stride, cudaStream_t st) {
+    if (n <= 0 || t <= 0 || !x) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
+    ld = round_up(t, 16);
+    buf.alloc((size_t)n * ld);
+    PICARD_CUDA(cudaMemcpy2DAsync(buf.p, sizeof(double) * ld, x, sizeof(double) * row_stride, sizeof(double) * t, n,
+                                  cudaMemcpyHostToDevice, st));
+  }
+};
+picard_config_t hook_config(int density_kind, double alpha, int ortho, int extended, double lambda_min, int device) {
+  picard_config_t c;
+  config_default(&c);
+  c.density_kind = density_kind; c.alpha = alpha; c.ortho = ortho; c.extended = extended; c.lambda_min = lambda_min; c.device = device;
+  return c;
+}
+}  // namespace
+
+struct picard_core {
+  int device;
+  cudaStream_t stream;
+  CoreSolver* solver;
+};
+
+extern "C" {
+
+int picard_abi_version(void) { return PICARD_B200_ABI_VERSION; }
+
+int picard_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* picard_status_string(int status) {
+  switch (status) {
+    case PICARD_OK: return "Ok";
+    case PICARD_INVALID_DIMENSIONS: return "Invalid dimensions";
+    case PICARD_SINGULAR_MATRIX: return "Singular matrix encountered during computation";
+    case PICARD_COMPUTATION_ERROR: return "Computation error";
+    case PICARD_INVALID_CONFIG: return "Invalid configuration";
+    default: return "Unknown status";
+  }
+}
+
+void picard_config_default(picard_config_t* cfg) { if (cfg) config_default(cfg); }
+
+int picard_config_validate(const picard_config_t* cfg, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!cfg) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'config': null pointer");
+    config_validate(*cfg);
+  });
+}
+
+int picard_fit(const double* x, int64_t n_features, int64_t n_samples, int64_t row_stride, const picard_config_t* cfg,
+               picard_result_t* out, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!out) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: null result pointer");
+    picard_config_t c;
+    if (cfg) c = *cfg; else config_default(&c);
+    try { fit_host(x, n_features, n_samples, row_stride, c, out); }
+    catch (...) { picard_result_free(out); throw; }
+  });
+}
+
+int picard_fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_t row_stride, const picard_config_t* cfg,
+                      double* d_sources, int64_t lds, picard_result_t* out, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!out) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: null result pointer");
+    picard_config_t c;
+    if (cfg) c = *cfg; else config_default(&c);
+    try { fit_device(d_x, n_features, n_samples, row_stride, c, d_sources, lds, out); }
+    catch (...) { picard_result_free(out); throw; }
+  });
+}
+
+int picard_transform(const double* x, int64_t n_features, int64_t n_samples, int64_t row_stride, const picard_result_t* result,
+                     double* out, int32_t device, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!result || !out || !result->unmixing) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: null result / output");
+    transform_host(x, n_features, n_samples, row_stride, *result, out, device);
+  });
+}
+
+void picard_result_free(picard_result_t* r) {
+  if (!r) return;
+  free(r->whitening); free(r->unmixing); free(r->sources); free(r->mean); free(r->signs);
+  r->whitening = r->unmixing = r->sources = r->mean = r->signs = nullptr;
+}
+
+// ---- resumable core -------------------------------------------------------------------------------
+int picard_core_create(picard_core_t** out, const double* d_x, int64_t n, int64_t n_samples, int64_t row_stride,
+                       const picard_config_t* cfg, int32_t covariance_identity, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!out || !cfg) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'config': null pointer");
+    config_validate(*cfg);
+    if (n <= 0 || n_samples <= 0) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
+    DeviceGuard guard(cfg->device);
+    picard_core* c = new picard_core();
+    c->device = guard.device; c->solver = nullptr; c->stream = nullptr;
+    try {
+      PICARD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      c->solver = new CoreSolver(d_x, (int)n, n_samples, row_stride, *cfg, covariance_identity != 0, guard.sm_count, c->stream);
+    } catch (...) {
+      if (c->stream) cudaStreamDestroy(c->stream);
+      delete c;
+      throw;
+    }
+    *out = c;
+  });
+}
+int picard_core_run(picard_core_t* c, int64_t max_new_iters, int64_t* iters_done, int32_t* converged, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (!c) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'core': null handle");
+    DeviceGuard guard(c->device);
+    int64_t d = c->solver->run(max_new_iters);
+    if (iters_done) *iters_done = d;
+    if (converged) *converged = c->solver->converged() ? 1 : 0;
+  });
+}
+int picard_core_reset(picard_core_t* c) {
+  return guarded(nullptr, 0, [&] { if (!c) throw Error(PICARD_INVALID_CONFIG, "null handle"); DeviceGuard guard(c->device); c->solver->reset(); });
+}
+int picard_core_state(picard_core_t* c, double* w, double* signs, int64_t* n_iterations, int32_t* converged, double* gradient_norm,
+                      double* loss) {
+  return guarded(nullptr, 0, [&] {
+    if (!c) throw Error(PICARD_INVALID_CONFIG, "null handle");
+    DeviceGuard guard(c->device);
+    c->solver->state(w, c->solver->extended() ? signs : nullptr, n_iterations, converged, gradient_norm, loss);
+  });
+}
+int picard_core_stats(picard_core_t* c, picard_stats_t* stats) {
+  if (!c || !stats) return PICARD_INVALID_CONFIG;
+  *stats = c->solver->stats();
+  return PICARD_OK;
+}
+void picard_core_destroy(picard_core_t* c) {
+  if (!c) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  delete c->solver;
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (prev >= 0) cudaSetDevice(prev);
+  delete c;
+}
+
+// ---- test hooks -----------------------------------------------------------------------------------
+int picard_eval_moments(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w, int32_t density_kind,
+                        double alpha, int32_t mode, int32_t want_h, int32_t device, double* gr, double* sd, double* hr, double* sq,
+                        double* lrow, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (mode < 0 || mode > 2) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'mode': must be 0, 1 or 2");
+    DeviceGuard guard(device);
+    Staged xs(x, n, n_samples, row_stride, 0);
+    PICARD_CUDA(cudaStreamSynchronize(0));
+    picard_config_t c = hook_config(density_kind, alpha, want_h ? 0 : 1, 0, 0.01, guard.device);
+    config_validate(c);
+    cudaStream_t st;
+    PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
+    CoreSolver solver(xs.buf.p, (int)n, n_samples, xs.ld, c, false, guard.sm_count, st);
+    solver.hook_moments(w, mode, want_h != 0, gr, sd, hr, sq, lrow);
+  });
+}
+
+int picard_eval_point(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w, int32_t density_kind,
+                      double alpha, int32_t ortho, int32_t extended, double lambda_min, const double* cmat, const double* old_signs,
+                      const double* loss_signs, int32_t device, double* g, double* h, double* hoff, double* signs,
+                      int32_t* sign_change, double* gradient_norm, double* loss, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    DeviceGuard guard(device);
+    Staged xs(x, n, n_samples, row_stride, 0);
+    PICARD_CUDA(cudaStreamSynchronize(0));
+    picard_config_t c = hook_config(density_kind, alpha, ortho, extended, lambda_min, guard.device);
+    config_validate(c);
+    cudaStream_t st;
+    PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
+    CoreSolver solver(xs.buf.p, (int)n, n_samples, xs.ld, c, false, guard.sm_count, st);
+    solver.hook_point(w, cmat, old_signs, loss_signs, g, h, hoff, signs, sign_change, gradient_norm, loss);
+  });
+}
+
+int picard_matrix_exp(const double* a, int64_t n64, double* out, int32_t device) {
+  return guarded(nullptr, 0, [&] {
+    DeviceGuard guard(device);
+    const int n = (int)n64;
+    const size_t nn = (size_t)n * n;
+    DevBuf<double> buf(8 * nn + 64);
+    double* b = buf.p;
+    small::ExpmWork w{b + nn, b + 2 * nn, b + 3 * nn, b + 4 * nn, b + 5 * nn, b + 7 * nn};
+    PICARD_CUDA(cudaMemcpy(b, a, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    double norm = 0;  // max |a|, ignoring NaN like the reference's fold(0.0, f64::max)
+    for (size_t i = 0; i < nn; ++i) norm = std::fmax(norm, std::fabs(a[i]));
+    small::matrix_exp(b, 1.0, norm, n, w, b + 6 * nn, 0);
+    PICARD_CUDA(cudaMemcpy(out, b + 6 * nn, sizeof(double) * nn, cudaMemcpyDeviceToHost));
+  });
+}
+
+int picard_sln_det(const double* m, int64_t n64, double* sign, double* logabs, int32_t device) {
+  return guarded(nullptr, 0, [&] {
+    DeviceGuard guard(device);
+    const int n = (int)n64;
+    const size_t nn = (size_t)n * n;
+    DevBuf<double> buf(2 * nn + 2);
+    PICARD_CUDA(cudaMemcpy(buf.p, m, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    small::sln_det(buf.p, n, buf.p + nn, buf.p + 2 * nn, 0);
+    double o[2];
+    PICARD_CUDA(cudaMemcpy(o, buf.p + 2 * nn, sizeof o, cudaMemcpyDeviceToHost));
+    if (logabs) *logabs = o[0];
+    if (sign) *sign = o[1];
+  });
+}
+
+int picard_sym_decorrelation(const double* w, int64_t n64, double* out, int32_t device) {
+  int status = PICARD_OK;
+  int rc = guarded(nullptr, 0, [&] {
+    DeviceGuard guard(device);
+    const int n = (int)n64;
+    const size_t nn = (size_t)n * n;
+    DevBuf<double> buf(6 * nn + n);
+    DevBuf<int> st(1);
+    PICARD_CUDA(cudaMemcpy(buf.p, w, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    small::sym_decorrelation(buf.p, n, buf.p + nn, buf.p + 5 * nn + n, st.p, 0);
+    PICARD_CUDA(cudaMemcpy(&status, st.p, sizeof(int), cudaMemcpyDeviceToHost));
+    PICARD_CUDA(cudaMemcpy(out, buf.p + 5 * nn + n, sizeof(double) * nn, cudaMemcpyDeviceToHost));
+  });
+  return rc != PICARD_OK ? rc : status;
+}
+
+int picard_compute_direction(const double* g, const double* h, const double* hoff, int64_t n64, const double* s_list,
+                             const double* y_list, const double* r_list, int64_t L, int32_t ortho, double* out, int32_t device) {
+  return guarded(nullptr, 0, [&] {
+    DeviceGuard guard(device);
+    const int n = (int)n64;
+    const size_t nn = (size_t)n * n;
+    const int m = (int)(L > 0 ? L : 1);
+    // front_kernel with do_lbfgs would recompute g/h; the direction is exercised through a dedicated tiny driver:
+    // state is laid out exactly as CoreSolver does and the two-loop part of the kernel runs on it.
+    DevBuf<double> buf(8 * nn + 3 * (size_t)n + 2 * nn * m + 2 * m + (size_t)mom_size(n) + MOM_EXTRA);
+    DevBuf<CoreScalars> sc(1);
+    buf.zero(0); sc.zero(0);
+    double* b = buf.p;
+    double *G = b, *Gtmp = b + nn, *Gold = b + 2 * nn, *H = b + 3 * nn, *S = b + 4 * nn, *q = b + 5 * nn, *D = b + 6 * nn, *C = b + 7 * nn;
+    double *ho = b + 8 * nn, *sg = ho + n, *os = sg + n, *ms = os + n, *my = ms + nn * m, *mr = my + nn * m, *mom = mr + 2 * m;
+    PICARD_CUDA(cudaMemcpy(G, g, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    PICARD_CUDA(cudaMemcpy(H, h, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    PICARD_CUDA(cudaMemcpy(ho, hoff, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (L > 0) {
+      PICARD_CUDA(cudaMemcpy(ms, s_list, sizeof(double) * nn * L, cudaMemcpyHostToDevice));
+      PICARD_CUDA(cudaMemcpy(my, y_list, sizeof(double) * nn * L, cudaMemcpyHostToDevice));
+      PICARD_CUDA(cudaMemcpy(mr, r_list, sizeof(double) * L, cudaMemcpyHostToDevice));
+    }
+    CoreScalars h_sc;
+    memset(&h_sc, 0, sizeof h_sc);
+    h_sc.mem_len = (int)L; h_sc.mem_head = 0;
+    PICARD_CUDA(cudaMemcpy(sc.p, &h_sc, sizeof h_sc, cudaMemcpyHostToDevice));
+    small::FrontArgs fa;
+    fa.d.n = n; fa.d.m = m; fa.d.t_total = 1.0; fa.d.ortho = ortho ? 1 : 0; fa.d.extended = 0; fa.d.lambda_min = 0.01;
+    fa.mom = mom; fa.C = C; fa.G = G; fa.Gtmp = Gtmp; fa.G_old = Gold; fa.H = H; fa.hoff = ho; fa.signs = sg; fa.old_signs = os;
+    fa.S_prev = S; fa.mem_s = ms; fa.mem_y = my; fa.mem_r = mr; fa.q = q; fa.D = D; fa.sc = sc.p; fa.first_iter = 1;
+    fa.do_lbfgs = 2;  // direction only, from the G / H / hoff already in place
+    small::iteration_front(fa, 0);
+    PICARD_CUDA(cudaMemcpy(out, D, sizeof(double) * nn, cudaMemcpyDeviceToHost));
+  });
+}
+
+int picard_center_whiten(const double* x, int64_t n_features, int64_t n_samples, int64_t row_stride, int64_t n_components,
+                         int32_t centering, int32_t device, double* mean, double* k, double* data, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    DeviceGuard guard(device);
+    cudaStream_t st;
+    PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
+    Staged xs(x, n_features, n_samples, row_stride, st);
+    std::vector<double> mh, kh;
+    picard_stats_t stats;
+    memset(&stats, 0, sizeof stats);
+    const int nf = (int)n_features, nc = (int)n_components;
+    center_whiten_device(xs.buf.p, nf, n_samples, xs.ld, nc, centering != 0, true, nullptr, guard.sm_count, st, mh, kh, (double)n_samples,
+                         &stats);
+    if (mean && centering) memcpy(mean, mh.data(), sizeof(double) * nf);
+    if (k) memcpy(k, kh.data(), sizeof(double) * nc * nf);
+    if (data) {
+      DevBuf<double> dy((size_t)nc * xs.ld);
+      apply_device(kh.data(), centering ? mh.data() : nullptr, nc, nf, xs.buf.p, xs.ld, dy.p, xs.ld, n_samples, guard.sm_count, st);
+      PICARD_CUDA(cudaMemcpy2DAsync(data, sizeof(double) * n_samples, dy.p, sizeof(double) * xs.ld, sizeof(double) * n_samples, nc,
+                                    cudaMemcpyDeviceToHost, st));
+      PICARD_CUDA(cudaStreamSynchronize(st));
+    }
+  });
+}
+
+int picard_jade(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, int64_t max_iter, double tol, int32_t verbose,
+                int32_t device, double* w, int64_t* sweeps, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    DeviceGuard guard(device);
+    cudaStream_t st;
+    PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
+    Staged xs(x, n, n_samples, row_stride, st);
+    picard_stats_t stats;
+    memset(&stats, 0, sizeof stats);
+    jade_device(xs.buf.p, (int)n, n_samples, xs.ld, (double)n_samples, max_iter, tol, verbose != 0, nullptr, guard.sm_count, st, w, sweeps,
+                &stats);
+  });
+}
+
+int picard_synth_sources(double* d_out, int64_t n, int64_t n_samples, int64_t ld, int64_t t_offset, int64_t n_laplace, uint64_t seed,
+                         int32_t device, void* stream) {
+  return guarded(nullptr, 0, [&] {
+    DeviceGuard guard(device);
+    aux::synth_sources(d_out, (int)n, n_samples, ld, t_offset, (int)n_laplace, seed, (cudaStream_t)stream);
+    PICARD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  });
+}
+
+int picard_apply_device(const double* a, const double* mean, int64_t n_out, int64_t n_in, const double* d_in, int64_t ld_in,
+                        double* d_out, int64_t ld_out, int64_t n_samples, int32_t device, void* stream) {
+  return guarded(nullptr, 0, [&] {
+    DeviceGuard guard(device);
+    apply_device(a, mean, (int)n_out, (int)n_in, d_in, ld_in, d_out, ld_out, n_samples, guard.sm_count, (cudaStream_t)stream);
+  });
+}
+
+// ---- communicator -----------------------------------------------------------------------------------
+int picard_comm_unique_id(char id[PICARD_UNIQUE_ID_BYTES]) {
+  return guarded(nullptr, 0, [&] { comm_unique_id(id); });
+}
+int picard_comm_create(picard_comm_t** out, const char id[PICARD_UNIQUE_ID_BYTES], int32_t rank, int32_t nranks, int32_t device,
+                       char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    DeviceGuard guard(device);
+    *out = comm_create(id, rank, nranks, guard.device);
+  });
+}
+int picard_comm_rank(const picard_comm_t* c) { return comm_rank(c); }
+int picard_comm_size(const picard_comm_t* c) { return comm_size(c); }
+void picard_comm_destroy(picard_comm_t* c) { comm_destroy(c); }
+
+}  // extern "C"

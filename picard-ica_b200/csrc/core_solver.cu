@@ -1,0 +1,303 @@
+// The core Picard loop (core.rs:162-401) with device-resident state.
+//
+// Control flow is the reference's, quirk for quirk; what differs is where the work happens:
+//   * every N x T quantity comes from the fused pass (pass.cuh) reading X once: Y is never materialised,
+//     the transform of a line-search try is folded into W (Y' = (M W) X),
+//   * line-search tries are SPECULATIVE: the first try of an iteration also accumulates the gradient
+//     moments of the trial point, so an accepted first try (the common case) makes the next iteration's
+//     gradient pass free.  Retries use the loss-only variant.  The iterate sequence is unchanged.
+//   * the per-row log-likelihood sums L_i are kept with each point, so the loss under new signs
+//     (core.rs:317-329) and the initial loss (core.rs:185) need no extra pass.
+#include "engine.cuh"
+
+namespace picard {
+
+DeviceGuard::DeviceGuard(int dev) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw Error(PICARD_COMPUTATION_ERROR,
+                "Computation error: no usable CUDA device (libpicard_b200 has no CPU fallback): " + std::string(cudaGetErrorString(e)));
+  PICARD_CUDA(cudaGetDevice(&prev));
+  device = dev < 0 ? prev : dev;
+  if (device >= count) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'device': no such CUDA device");
+  PICARD_CUDA(cudaSetDevice(device));
+  PICARD_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+}
+DeviceGuard::~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+
+CoreSolver::CoreSolver(const double* d_x, int n, int64_t t_local, int64_t ldx, const picard_config_t& cfg, bool covariance_identity,
+                       int sm_count, cudaStream_t stream)
+    : cfg_(cfg), d_x_(d_x), t_local_(t_local), ldx_(ldx), sm_count_(sm_count), st_(stream), comm_(cfg.comm),
+      cov_identity_(covariance_identity), sc_dev_(1), sc_host_(1) {
+  dims_.n = n;
+  dims_.m = (int)cfg.m;
+  dims_.ortho = cfg.ortho ? 1 : 0;
+  dims_.extended = (cfg.extended < 0 ? cfg.ortho : cfg.extended) ? 1 : 0;
+  dims_.lambda_min = cfg.lambda_min;
+  // global sample count (core.rs:176 `t as f64`, with T the total over all shards)
+  double tt = (double)t_local;
+  if (comm_ && comm_size(comm_) > 1) {
+    DevBuf<double> tmp(1);
+    PICARD_CUDA(cudaMemcpyAsync(tmp.p, &tt, sizeof(double), cudaMemcpyHostToDevice, st_));
+    comm_allreduce_sum(comm_, tmp.p, 1, st_);
+    PICARD_CUDA(cudaMemcpyAsync(&tt, tmp.p, sizeof(double), cudaMemcpyDeviceToHost, st_));
+    PICARD_CUDA(cudaStreamSynchronize(st_));
+  }
+  dims_.t_total = tt;
+  dens_ = cfg.density_kind;
+  alpha_ = (dens_ == PICARD_DENSITY_CUBE) ? 1.0 : cfg.alpha;
+  need_h_ = !dims_.ortho;
+  pass_padded_size(n);  // validates n
+
+  const size_t nn = (size_t)n * n;
+  const size_t msz = (size_t)mom_size(n) + MOM_EXTRA;
+  size_t total = 0;
+  auto take = [&](size_t count) { size_t o = total; total += (count + 1) & ~(size_t)1; return o; };
+  const size_t oW = take(nn), oWt = take(nn), oM = take(nn), oD = take(nn), oC = take(nn), oG = take(nn), oGt = take(nn),
+               oGo = take(nn), oH = take(nn), oho = take(n), osg = take(n), oos = take(n), oSp = take(nn), oq = take(nn),
+               oms = take(nn * dims_.m), omy = take(nn * dims_.m), omr = take(2 * (size_t)dims_.m), omc = take(msz), omt = take(msz),
+               olu = take(nn), oAs = take(nn), ot0 = take(nn), ot1 = take(nn), or0 = take(nn), or1 = take(nn), osl = take(32);
+  store_.alloc(total);
+  store_.zero(st_);
+  double* b = store_.p;
+  W_ = b + oW; Wt_ = b + oWt; M_ = b + oM; D_ = b + oD; C_ = b + oC; G_ = b + oG; Gtmp_ = b + oGt; Gold_ = b + oGo; H_ = b + oH;
+  hoff_ = b + oho; signs_ = b + osg; old_signs_ = b + oos; Sprev_ = b + oSp; q_ = b + oq; mem_s_ = b + oms; mem_y_ = b + omy;
+  mem_r_ = b + omr; mom_cur_ = b + omc; mom_trial_ = b + omt; lu_work_ = b + olu;
+  ew_.As = b + oAs; ew_.term0 = b + ot0; ew_.term1 = b + ot1; ew_.res0 = b + or0; ew_.res1 = b + or1; ew_.slots = b + osl;
+  partial_.alloc(pass_workspace_doubles(n, sm_count_));
+  PICARD_CUDA(cudaEventCreate(&ev_a_));
+  PICARD_CUDA(cudaEventCreate(&ev_b_));
+  PICARD_CUDA(cudaEventCreate(&ev_run0_));
+  PICARD_CUDA(cudaEventCreate(&ev_run1_));
+  memset(&stats_, 0, sizeof stats_);
+  reset();
+}
+
+CoreSolver::~CoreSolver() {
+  cudaEventDestroy(ev_a_); cudaEventDestroy(ev_b_); cudaEventDestroy(ev_run0_); cudaEventDestroy(ev_run1_);
+}
+
+void CoreSolver::reset() {
+  const int n = dims_.n;
+  store_.zero(st_);
+  sc_dev_.zero(st_);
+  stats_.kernel_launches += small::set_identity(W_, n, st_);       // core.rs:178
+  stats_.kernel_launches += small::set_identity(C_, n, st_);       // core.rs:204 (replaced below when extended)
+  std::vector<double> ones((size_t)n, 1.0);
+  PICARD_CUDA(cudaMemcpyAsync(signs_, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st_));      // core.rs:182
+  PICARD_CUDA(cudaMemcpyAsync(old_signs_, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st_));  // core.rs:183
+  PICARD_CUDA(cudaStreamSynchronize(st_));
+  iter_ = 0; n_iterations_ = 0; converged_ = false; started_ = false; have_cur_ = false; speculate_next_ = true;
+  gradient_norm_ = 1.0; current_loss_ = 0.0;
+}
+
+void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, double alpha, double* d_mom) {
+  PassLaunch L;
+  L.d_x = d_x_; L.ldx = ldx_; L.t_local = t_local_; L.n_in = dims_.n; L.n_out = dims_.n;
+  L.d_w = d_w; L.ldw = dims_.n; L.d_bias = nullptr; L.dens = dens; L.alpha = alpha; L.mode = mode; L.want_h = want_h;
+  L.d_partial = partial_.p; L.d_mom = d_mom; L.d_out = nullptr; L.ld_out = 0; L.sm_count = sm_count_; L.stream = st_;
+  PICARD_CUDA(cudaEventRecord(ev_a_, st_));
+  stats_.kernel_launches += launch_pass(L);
+  PICARD_CUDA(cudaEventRecord(ev_b_, st_));
+  // one NCCL allreduce of exactly what this pass produced
+  if (comm_ && comm_size(comm_) > 1) {
+    const int n = dims_.n;
+    const size_t nn = (size_t)n * n;
+    if (mode == PASS_LOSS) comm_allreduce_sum(comm_, d_mom + mom_off_sq(n), 2 * (size_t)n, st_);
+    else if (mode == PASS_FUSED) comm_allreduce_sum(comm_, d_mom, nn + 3 * (size_t)n + (want_h ? nn : 0), st_);
+    else comm_allreduce_sum2(comm_, d_mom, nn + 2 * (size_t)n, want_h ? d_mom + mom_off_hr(n) : nullptr, want_h ? nn : 0, st_);
+  }
+  last_pass_mode_ = mode;
+}
+
+void CoreSolver::pass(const double* d_w, int mode, double* d_mom) {
+  if (mode == PASS_FUSED) stats_.fused_passes++;
+  else if (mode == PASS_GRAD) stats_.grad_passes++;
+  else stats_.loss_passes++;
+  eval_pass(d_w, mode, need_h_ && mode != PASS_LOSS, dens_, alpha_, d_mom);
+}
+
+void CoreSolver::fetch_scalars() {
+  PICARD_CUDA(cudaMemcpyAsync(sc_host_.p, sc_dev_.p, sizeof(CoreScalars), cudaMemcpyDeviceToHost, st_));
+  PICARD_CUDA(cudaStreamSynchronize(st_));
+  // the last pass has certainly finished: account its device time
+  float ms = 0.f;
+  if (last_pass_mode_ >= 0 && cudaEventElapsedTime(&ms, ev_a_, ev_b_) == cudaSuccess) {
+    if (last_pass_mode_ == PASS_FUSED) stats_.pass_ms_fused += ms;
+    else if (last_pass_mode_ == PASS_GRAD) stats_.pass_ms_grad += ms;
+    else if (last_pass_mode_ == PASS_LOSS) stats_.pass_ms_loss += ms;
+  }
+  last_pass_mode_ = -1;
+}
+
+// One line-search try (core.rs:118-128): transform, W' = M W, pass at W', loss, accept flag -> scalars on host.
+void CoreSolver::try_point(double alpha, bool speculate) {
+  const int n = dims_.n;
+  stats_.ls_tries++;
+  if (dims_.ortho) {
+    stats_.kernel_launches += small::matrix_exp(D_, alpha, sc_host_.p->norm_d, n, ew_, M_, st_);  // core.rs:119
+  } else {
+    stats_.kernel_launches += small::eye_plus_scaled(D_, alpha, M_, n, st_);                      // core.rs:121
+  }
+  stats_.kernel_launches += small::matmul(M_, W_, Wt_, n, false, 1.0, false, st_);                // core.rs:125
+  if (!dims_.ortho)  // -log|det W'| term of the loss (core.rs:51-70)
+    stats_.kernel_launches += small::sln_det(Wt_, n, lu_work_, mom_trial_ + mom_size(n), st_);
+  pass(Wt_, speculate ? PASS_FUSED : PASS_LOSS, mom_trial_);                                      // core.rs:124,127
+  stats_.kernel_launches += small::loss_from_moments(dims_, mom_trial_, signs_, sc_dev_.p, 0, st_);
+  fetch_scalars();
+}
+
+int64_t CoreSolver::run(int64_t max_new) {
+  const int n = dims_.n;
+  const bool no_spec = (cfg_.flags & PICARD_FLAG_NO_SPECULATION) != 0;
+  PICARD_CUDA(cudaEventRecord(ev_run0_, st_));
+  if (!started_) {
+    // initial loss with signs = 1 (core.rs:185-194, quirk Q1); the same pass already yields the first gradient
+    if (!dims_.ortho) stats_.kernel_launches += small::sln_det(W_, n, lu_work_, mom_cur_ + mom_size(n), st_);
+    pass(W_, no_spec ? PASS_LOSS : PASS_FUSED, mom_cur_);
+    have_cur_ = !no_spec;
+    stats_.kernel_launches += small::loss_from_moments(dims_, mom_cur_, nullptr, sc_dev_.p, 1, st_);
+    fetch_scalars();
+    if (sc_host_.p->loss_singular) throw Error(PICARD_SINGULAR_MATRIX, "Singular matrix encountered during computation");
+    current_loss_ = sc_host_.p->current_loss;
+    if (dims_.extended && !cov_identity_) {
+      // C = Y Y^T / T once, never updated (core.rs:199-205, quirk Q5): a LINEAR gradient pass gives sum y y^T
+      eval_pass(W_, PASS_GRAD, false, DENS_LINEAR, 1.0, mom_trial_);
+      stats_.grad_passes++;
+      stats_.kernel_launches += small::copy_scaled(mom_trial_ + mom_off_gr(n), C_, (int64_t)n * n, 1.0 / dims_.t_total, st_);
+    }
+    started_ = true;
+  }
+  int64_t done = 0;
+  while (done < max_new && iter_ < cfg_.max_iter && !converged_) {
+    if (!have_cur_) {  // gradient moments of the current iterate are missing (a loss-only try was accepted)
+      pass(W_, PASS_GRAD, mom_cur_);
+      have_cur_ = true;
+    }
+    small::FrontArgs fa;
+    fa.d = dims_; fa.mom = mom_cur_; fa.C = C_; fa.G = G_; fa.Gtmp = Gtmp_; fa.G_old = Gold_; fa.H = H_; fa.hoff = hoff_;
+    fa.signs = signs_; fa.old_signs = old_signs_; fa.S_prev = Sprev_; fa.mem_s = mem_s_; fa.mem_y = mem_y_; fa.mem_r = mem_r_;
+    fa.q = q_; fa.D = D_; fa.sc = sc_dev_.p; fa.first_iter = (iter_ == 0) ? 1 : 0; fa.do_lbfgs = 1;
+    stats_.kernel_launches += small::iteration_front(fa, st_);
+    fetch_scalars();
+    gradient_norm_ = sc_host_.p->gradient_norm;
+    if (sc_host_.p->sign_change) stats_.sign_changes++;
+    n_iterations_ = iter_ + 1;                              // core.rs:212,396 (quirk Q10)
+    if (gradient_norm_ < cfg_.tol) { converged_ = true; break; }  // core.rs:289-293
+    current_loss_ = sc_host_.p->current_loss;
+
+    // ---- backtracking line search (core.rs:99-150)
+    double alpha = 1.0;
+    bool success = false;
+    bool last_spec = false;
+    bool first_try_ok = false;
+    for (int64_t t = 0; t < cfg_.ls_tries; ++t) {
+      last_spec = !no_spec && t == 0 && speculate_next_;
+      try_point(alpha, last_spec);
+      if (sc_host_.p->accept) { success = true; first_try_ok = (t == 0); break; }
+      alpha /= 2.0;
+    }
+    if (!success) {  // gradient-descent fallback (core.rs:349-367, quirk Q3): 10 tries, result taken regardless
+      stats_.fallbacks++;
+      stats_.kernel_launches += small::negate_into(G_, D_, (int64_t)n * n, sc_dev_.p, st_);  // also clears the memory
+      sc_host_.p->norm_d = gradient_norm_;
+      alpha = 1.0;
+      for (int t = 0; t < 10; ++t) {
+        last_spec = false;
+        try_point(alpha, false);
+        if (sc_host_.p->accept) { success = true; break; }
+        alpha /= 2.0;
+      }
+    }
+    // step = direction * alpha (on failure alpha has been halved once more: quirk Q2)
+    stats_.kernel_launches += small::accept_step(dims_, D_, alpha, Sprev_, Wt_, C_, (dims_.extended && cov_identity_) ? 1 : 0,
+                                                 sc_dev_.p, st_);
+    std::swap(W_, Wt_);
+    std::swap(mom_cur_, mom_trial_);
+    have_cur_ = last_spec;
+    speculate_next_ = first_try_ok;
+    current_loss_ = sc_host_.p->new_loss;
+    if (cfg_.verbose) {
+      auto e4 = [](double v) {
+        char buf[64]; snprintf(buf, sizeof buf, "%.4e", v);
+        std::string s(buf); size_t e = s.find('e');
+        if (e == std::string::npos) return s;
+        return s.substr(0, e) + "e" + std::to_string(atoi(s.c_str() + e + 1));
+      };
+      if (!comm_ || comm_rank(comm_) == 0) {
+        printf("iteration %lld, gradient norm = %s, loss = %s\n", (long long)(iter_ + 1), e4(gradient_norm_).c_str(),
+               e4(current_loss_).c_str());
+        fflush(stdout);
+      }
+    }
+    ++iter_;
+    ++done;
+  }
+  PICARD_CUDA(cudaEventRecord(ev_run1_, st_));
+  PICARD_CUDA(cudaStreamSynchronize(st_));
+  float ms = 0.f;
+  PICARD_CUDA(cudaEventElapsedTime(&ms, ev_run0_, ev_run1_));
+  stats_.core_ms += ms;
+  return done;
+}
+
+void CoreSolver::hook_moments(const double* w_host, int mode, bool want_h, double* gr, double* sd, double* hr, double* sq,
+                              double* lrow) {
+  const int n = dims_.n;
+  const size_t nn = (size_t)n * n;
+  if (w_host) PICARD_CUDA(cudaMemcpyAsync(W_, w_host, sizeof(double) * nn, cudaMemcpyHostToDevice, st_));
+  eval_pass(W_, mode, want_h, dens_, alpha_, mom_cur_);
+  auto get = [&](double* dst, int64_t off, size_t cnt) {
+    if (dst) PICARD_CUDA(cudaMemcpyAsync(dst, mom_cur_ + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st_));
+  };
+  if (mode != PASS_LOSS) { get(gr, mom_off_gr(n), nn); get(sd, mom_off_sd(n), n); if (want_h) get(hr, mom_off_hr(n), nn); }
+  get(sq, mom_off_sq(n), n);
+  if (mode != PASS_GRAD) get(lrow, mom_off_ll(n), n);
+  PICARD_CUDA(cudaStreamSynchronize(st_));
+}
+
+void CoreSolver::hook_point(const double* w_host, const double* c_host, const double* old_signs_host, const double* loss_signs_host,
+                            double* g, double* h, double* hoff, double* signs, int32_t* sign_change, double* gradient_norm,
+                            double* loss) {
+  const int n = dims_.n;
+  const size_t nn = (size_t)n * n;
+  if (w_host) PICARD_CUDA(cudaMemcpyAsync(W_, w_host, sizeof(double) * nn, cudaMemcpyHostToDevice, st_));
+  if (c_host) PICARD_CUDA(cudaMemcpyAsync(C_, c_host, sizeof(double) * nn, cudaMemcpyHostToDevice, st_));
+  if (old_signs_host) PICARD_CUDA(cudaMemcpyAsync(old_signs_, old_signs_host, sizeof(double) * n, cudaMemcpyHostToDevice, st_));
+  if (!dims_.ortho) stats_.kernel_launches += small::sln_det(W_, n, lu_work_, mom_cur_ + mom_size(n), st_);
+  eval_pass(W_, PASS_FUSED, need_h_, dens_, alpha_, mom_cur_);
+  small::FrontArgs fa;
+  fa.d = dims_; fa.mom = mom_cur_; fa.C = C_; fa.G = G_; fa.Gtmp = Gtmp_; fa.G_old = Gold_; fa.H = H_; fa.hoff = hoff_;
+  fa.signs = signs_; fa.old_signs = old_signs_; fa.S_prev = Sprev_; fa.mem_s = mem_s_; fa.mem_y = mem_y_; fa.mem_r = mem_r_;
+  fa.q = q_; fa.D = D_; fa.sc = sc_dev_.p; fa.first_iter = old_signs_host ? 0 : 1; fa.do_lbfgs = 0;
+  stats_.kernel_launches += small::iteration_front(fa, st_);
+  const double* ls = signs_;
+  if (loss_signs_host) {
+    PICARD_CUDA(cudaMemcpyAsync(q_, loss_signs_host, sizeof(double) * n, cudaMemcpyHostToDevice, st_));
+    ls = q_;
+  }
+  stats_.kernel_launches += small::loss_from_moments(dims_, mom_cur_, ls, sc_dev_.p, 1, st_);
+  fetch_scalars();
+  auto get = [&](double* dst, const double* src, size_t cnt) {
+    if (dst) PICARD_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st_));
+  };
+  get(g, G_, nn); get(h, H_, nn); get(hoff, hoff_, n); get(signs, signs_, n);
+  PICARD_CUDA(cudaStreamSynchronize(st_));
+  if (sign_change) *sign_change = sc_host_.p->sign_change;
+  if (gradient_norm) *gradient_norm = sc_host_.p->gradient_norm;
+  if (loss) *loss = sc_host_.p->current_loss;
+}
+
+void CoreSolver::state(double* w, double* signs, int64_t* n_iterations, int32_t* converged, double* gradient_norm, double* loss) {
+  const int n = dims_.n;
+  if (w) PICARD_CUDA(cudaMemcpyAsync(w, W_, sizeof(double) * n * n, cudaMemcpyDeviceToHost, st_));
+  if (signs) PICARD_CUDA(cudaMemcpyAsync(signs, signs_, sizeof(double) * n, cudaMemcpyDeviceToHost, st_));
+  PICARD_CUDA(cudaStreamSynchronize(st_));
+  if (n_iterations) *n_iterations = n_iterations_;
+  if (converged) *converged = converged_ ? 1 : 0;
+  if (gradient_norm) *gradient_norm = gradient_norm_;
+  if (loss) *loss = current_loss_;
+}
+
+}  // namespace picard

@@ -1,0 +1,339 @@
+// The fit pipeline: Picard::fit_with_config (solver.rs:45-189), Picard::transform (solver.rs:199-214),
+// centering + whitening (whitening.rs:24-116) with every N x T step on the device.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <random>
+
+#include "engine.cuh"
+#include "jade.cuh"
+
+namespace picard {
+
+void config_default(picard_config_t* c) {  // config.rs:64-85
+  memset(c, 0, sizeof *c);
+  c->density_kind = PICARD_DENSITY_TANH; c->alpha = 1.0;
+  c->n_components = -1; c->ortho = 1; c->extended = -1; c->whiten = 1; c->centering = 1;
+  c->max_iter = 500; c->tol = 1e-7; c->m = 7; c->ls_tries = 10; c->lambda_min = 0.01;
+  c->w_init = nullptr; c->w_init_rows = 0; c->w_init_cols = 0; c->fastica_it = -1; c->jade_it = -1;
+  c->has_seed = 0; c->seed = 0; c->verbose = 0; c->device = -1; c->comm = nullptr; c->flags = 0;
+}
+
+void config_validate(const picard_config_t& c) {  // config.rs:104-142, same order, same messages
+  auto fail = [](const char* param, const char* msg) {
+    throw Error(PICARD_INVALID_CONFIG, std::string("Invalid configuration for '") + param + "': " + msg);
+  };
+  if (c.max_iter <= 0) fail("max_iter", "must be greater than 0");
+  if (!(c.tol > 0.0)) fail("tol", "must be positive");
+  if (!(c.lambda_min > 0.0)) fail("lambda_min", "must be positive");
+  if (c.m <= 0) fail("m", "L-BFGS memory size must be at least 1");
+  if (c.fastica_it >= 0 && c.jade_it >= 0) fail("jade_it", "cannot use both fastica_it and jade_it; choose one warm start method");
+  if (c.density_kind < 0 || c.density_kind > 2) fail("density", "unknown density kind");
+}
+
+// splitmix64 stream; u = ((next >> 11) + 0.5) 2^-53; Box-Muller, both outputs used in order.  This is the
+// build's own generator (the reference's rand 0.9 ChaCha12/Ziggurat stream is not reproducible here):
+// same distribution, different stream.  Parity runs pass w_init explicitly.
+void randn_fill(uint64_t seed, double* out, size_t count) {
+  uint64_t s = seed;
+  auto next = [&]() { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
+  auto uni = [&]() { return ((double)(next() >> 11) + 0.5) * (1.0 / 9007199254740992.0); };
+  size_t i = 0;
+  while (i < count) {
+    const double u1 = uni(), u2 = uni();
+    const double r = std::sqrt(-2.0 * std::log(u1)), a = 6.283185307179586476925286766559 * u2;
+    out[i++] = r * std::cos(a);
+    if (i < count) out[i++] = r * std::sin(a);
+  }
+}
+
+static void host_matmul(const double* a, const double* b, double* c, int m, int k, int n) {
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < n; ++j) {
+      double s = 0;
+      for (int l = 0; l < k; ++l) s += a[(size_t)i * k + l] * b[(size_t)l * n + j];
+      c[(size_t)i * n + j] = s;
+    }
+}
+
+int apply_device(const double* a_host, const double* mean_host, int n_out, int n_in, const double* d_in, int64_t ld_in,
+                 double* d_out, int64_t ld_out, int64_t t_local, int sm_count, cudaStream_t st) {
+  if ((ld_out & 1) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+    throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: device output must be 16-byte aligned with an even row stride");
+  DevBuf<double> dA((size_t)n_out * n_in), dB((size_t)n_out);
+  std::vector<double> bias((size_t)n_out, 0.0);
+  if (mean_host)
+    for (int i = 0; i < n_out; ++i) { double s = 0; for (int k = 0; k < n_in; ++k) s += a_host[(size_t)i * n_in + k] * mean_host[k]; bias[i] = s; }
+  PICARD_CUDA(cudaMemcpyAsync(dA.p, a_host, sizeof(double) * n_out * n_in, cudaMemcpyHostToDevice, st));
+  PICARD_CUDA(cudaMemcpyAsync(dB.p, bias.data(), sizeof(double) * n_out, cudaMemcpyHostToDevice, st));
+  PassLaunch L;
+  L.d_x = d_in; L.ldx = ld_in; L.t_local = t_local; L.n_in = n_in; L.n_out = n_out; L.d_w = dA.p; L.ldw = n_in;
+  L.d_bias = mean_host ? dB.p : nullptr; L.dens = DENS_LINEAR; L.alpha = 1.0; L.mode = PASS_APPLY; L.want_h = false;
+  L.d_partial = nullptr; L.d_mom = nullptr; L.d_out = d_out; L.ld_out = ld_out; L.sm_count = sm_count; L.stream = st;
+  int launches = launch_pass(L);
+  PICARD_CUDA(cudaStreamSynchronize(st));  // dA / dB go out of scope
+  return launches;
+}
+
+void center_whiten_device(const double* d_x, int nf, int64_t t_local, int64_t ldx, int nc, bool centering, bool whiten,
+                          picard_comm* comm, int sm_count, cudaStream_t st, std::vector<double>& mean_host,
+                          std::vector<double>& k_host, double t_total, picard_stats_t* stats) {
+  mean_host.clear();
+  k_host.clear();
+  DevBuf<double> dmean((size_t)nf);
+  dmean.zero(st);
+  if (centering) {  // center: whitening.rs:24-35 (row means; the subtraction is folded into the passes as a bias)
+    DevBuf<double> work((size_t)nf * 1024);
+    stats->kernel_launches += aux::row_sums(d_x, nf, t_local, ldx, work.p, dmean.p, st);
+    comm_allreduce_sum(comm, dmean.p, (size_t)nf, st);
+    mean_host.resize((size_t)nf);
+    PICARD_CUDA(cudaMemcpyAsync(mean_host.data(), dmean.p, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+    PICARD_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < nf; ++i) mean_host[i] /= t_total;
+    PICARD_CUDA(cudaMemcpyAsync(dmean.p, mean_host.data(), sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+  }
+  if (!whiten) return;
+  if (nc > nf)  // whitening.rs:51-58
+    throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: n_components (" + std::to_string(nc) + ") cannot exceed n_features (" +
+                                               std::to_string(nf) + ")");
+  // whiten: whitening.rs:48-116.  The thin SVD of the N x T matrix (dgesvd, U and s only) is replaced by the
+  // symmetric eigenproblem of X_c X_c^T = U S^2 U^T: a SYRK-shaped pass (the moments kernel with psi(y) = y,
+  // W = I, bias = mean) + one allreduce + a single-CTA Jacobi eigensolver.
+  const size_t nn = (size_t)nf * nf;
+  DevBuf<double> eye(nn), mom((size_t)mom_size(nf) + MOM_EXTRA), partial(pass_workspace_doubles(nf, sm_count)), V(nn), ev((size_t)nf);
+  stats->kernel_launches += small::set_identity(eye.p, nf, st);
+  PassLaunch L;
+  L.d_x = d_x; L.ldx = ldx; L.t_local = t_local; L.n_in = nf; L.n_out = nf; L.d_w = eye.p; L.ldw = nf;
+  L.d_bias = centering ? dmean.p : nullptr; L.dens = DENS_LINEAR; L.alpha = 1.0; L.mode = PASS_GRAD; L.want_h = false;
+  L.d_partial = partial.p; L.d_mom = mom.p; L.d_out = nullptr; L.ld_out = 0; L.sm_count = sm_count; L.stream = st;
+  stats->kernel_launches += launch_pass(L);
+  comm_allreduce_sum(comm, mom.p + mom_off_gr(nf), nn, st);
+  stats->kernel_launches += small::jacobi_eigh(mom.p + mom_off_gr(nf), nf, V.p, ev.p, st);
+  std::vector<double> evals((size_t)nf), U(nn);
+  PICARD_CUDA(cudaMemcpyAsync(evals.data(), ev.p, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+  PICARD_CUDA(cudaMemcpyAsync(U.data(), V.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
+  PICARD_CUDA(cudaStreamSynchronize(st));
+  // singular values descending = sqrt of eigenvalues descending (dgesvd order); min over the kept ones (whitening.rs:72-79)
+  double min_sv = INFINITY;
+  for (int i = 0; i < nc; ++i) min_sv = std::fmin(min_sv, std::sqrt(std::fmax(evals[nf - 1 - i], 0.0)));
+  if (!(min_sv >= 1e-10)) throw Error(PICARD_SINGULAR_MATRIX, "Singular matrix encountered during computation");
+  const double scale = std::sqrt(t_total);  // whitening.rs:83
+  k_host.assign((size_t)nc * nf, 0.0);
+  for (int i = 0; i < nc; ++i) {
+    const int col = nf - 1 - i;
+    const double s = std::sqrt(evals[col]);
+    for (int j = 0; j < nf; ++j) k_host[(size_t)i * nf + j] = U[(size_t)j * nf + col] / s * scale;
+    // sign rule, whitening.rs:93-107 (quirk Q16; Iterator::max_by keeps the LAST maximum on ties)
+    int best = 0;
+    for (int j = 0; j < nf; ++j)
+      if (std::fabs(k_host[(size_t)i * nf + j]) >= std::fabs(k_host[(size_t)i * nf + best])) best = j;
+    if (k_host[(size_t)i * nf + best] < 0.0)
+      for (int j = 0; j < nf; ++j) k_host[(size_t)i * nf + j] = -k_host[(size_t)i * nf + j];
+  }
+}
+
+static double* dup_host(const double* p, size_t n) {
+  double* o = (double*)malloc(sizeof(double) * (n ? n : 1));
+  if (!o) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: out of host memory");
+  memcpy(o, p, sizeof(double) * n);
+  return o;
+}
+
+void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_t ldx, const picard_config_t& cfg,
+                double* d_sources, int64_t lds, picard_result_t* out) {
+  memset(out, 0, sizeof *out);
+  config_validate(cfg);                                                       // solver.rs:46
+  if (n_features <= 0 || n_samples <= 0)                                      // solver.rs:50-54
+    throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
+  if (cfg.fastica_it >= 0)
+    throw Error(PICARD_COMPUTATION_ERROR, "Computation error: the FastICA warm start (fastica_it) is not implemented on the device yet");
+  DeviceGuard guard(cfg.device);
+  cudaStream_t st;
+  PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
+  cudaEvent_t e0, e1;
+  PICARD_CUDA(cudaEventCreate(&e0)); PICARD_CUDA(cudaEventCreate(&e1));
+  struct EvDel { cudaEvent_t a, b; ~EvDel() { cudaEventDestroy(a); cudaEventDestroy(b); } } edel{e0, e1};
+  PICARD_CUDA(cudaEventRecord(e0, st));
+  picard_stats_t stats;
+  memset(&stats, 0, sizeof stats);
+
+  const int nf = (int)n_features;
+  const int64_t t_local = n_samples;
+  double t_total = (double)t_local;
+  if (cfg.comm && comm_size(cfg.comm) > 1) {
+    DevBuf<double> tmp(1);
+    PICARD_CUDA(cudaMemcpyAsync(tmp.p, &t_total, sizeof(double), cudaMemcpyHostToDevice, st));
+    comm_allreduce_sum(cfg.comm, tmp.p, 1, st);
+    PICARD_CUDA(cudaMemcpyAsync(&t_total, tmp.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PICARD_CUDA(cudaStreamSynchronize(st));
+  }
+  const int64_t mn = std::min<int64_t>(nf, (int64_t)t_total);
+  int64_t ncomp = cfg.n_components >= 0 ? cfg.n_components : mn;              // solver.rs:63
+  if (ncomp > mn) ncomp = mn;
+  const bool ortho = cfg.ortho != 0;
+  const bool extended = cfg.extended < 0 ? ortho : (cfg.extended != 0);      // solver.rs:66
+  if (cfg.density_kind != PICARD_DENSITY_TANH && extended && !ortho && (!cfg.comm || comm_rank(cfg.comm) == 0))  // solver.rs:69-74
+    fprintf(stderr, "Warning: Using a density other than tanh with extended=true and ortho=false may result in incorrect estimation or numerical overflow\n");
+
+  std::vector<double> mean, K;
+  center_whiten_device(d_x, nf, t_local, ldx, (int)ncomp, cfg.centering != 0, cfg.whiten != 0, cfg.comm, guard.sm_count, st, mean, K,
+                       t_total, &stats);                                      // solver.rs:77-93
+  const int nc = cfg.whiten ? (int)ncomp : nf;                                // solver.rs:95 (quirk Q13)
+  pass_padded_size(nc);
+
+  // w_init (solver.rs:98-121)
+  std::vector<double> w_init((size_t)nc * nc);
+  if (cfg.w_init) {
+    if ((cfg.w_init_rows || cfg.w_init_cols) && (cfg.w_init_rows != nc || cfg.w_init_cols != nc))
+      throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: w_init shape [" + std::to_string(cfg.w_init_rows) + ", " +
+                                                 std::to_string(cfg.w_init_cols) + "] doesn't match expected (" + std::to_string(nc) +
+                                                 ", " + std::to_string(nc) + ")");
+    memcpy(w_init.data(), cfg.w_init, sizeof(double) * nc * nc);
+  } else {
+    uint64_t seed = cfg.seed;
+    if (!cfg.has_seed) { std::random_device rd; seed = ((uint64_t)rd() << 32) ^ rd(); }
+    std::vector<double> g((size_t)nc * nc);
+    randn_fill(seed, g.data(), g.size());
+    DevBuf<double> dg((size_t)nc * nc), dwork(4 * (size_t)nc * nc + nc), dout((size_t)nc * nc);
+    DevBuf<int> dst(1);
+    PICARD_CUDA(cudaMemcpyAsync(dg.p, g.data(), sizeof(double) * nc * nc, cudaMemcpyHostToDevice, st));
+    stats.kernel_launches += small::sym_decorrelation(dg.p, nc, dwork.p, dout.p, dst.p, st);
+    int status = 0;
+    PICARD_CUDA(cudaMemcpyAsync(&status, dst.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PICARD_CUDA(cudaMemcpyAsync(w_init.data(), dout.p, sizeof(double) * nc * nc, cudaMemcpyDeviceToHost, st));
+    PICARD_CUDA(cudaStreamSynchronize(st));
+    if (status != PICARD_OK) throw Error(PICARD_SINGULAR_MATRIX, "Singular matrix encountered during computation");
+  }
+
+  // x1 = K (x - mean) when a warm start needs the whitened data itself (solver.rs:124-137)
+  const int64_t ld1 = round_up(t_local, 16);
+  DevBuf<double> x1((size_t)nc * ld1);
+  std::vector<double> eye_nc;
+  if (cfg.jade_it >= 0) {
+    if (cfg.verbose && (!cfg.comm || comm_rank(cfg.comm) == 0)) printf("Running %lld iterations of JADE...\n", (long long)cfg.jade_it);
+    std::vector<double> a0;
+    const double* a_ptr;
+    if (cfg.whiten) a_ptr = K.data();
+    else { a0.assign((size_t)nc * nc, 0.0); for (int i = 0; i < nc; ++i) a0[(size_t)i * nc + i] = 1.0; a_ptr = a0.data(); }
+    stats.kernel_launches += apply_device(a_ptr, mean.empty() ? nullptr : mean.data(), nc, nf, d_x, ldx, x1.p, ld1, t_local,
+                                          guard.sm_count, st);
+    jade_device(x1.p, nc, t_local, ld1, t_total, cfg.jade_it, 1e-6, cfg.verbose != 0, cfg.comm, guard.sm_count, st, w_init.data(),
+                nullptr, &stats);                                             // replaces w_init (quirk Q14)
+  }
+
+  // x1 = w_init * K * (x - mean)  (solver.rs:140 with whitening.rs:110 folded in)
+  std::vector<double> a_total((size_t)nc * nf);
+  if (cfg.whiten) host_matmul(w_init.data(), K.data(), a_total.data(), nc, nc, nf);
+  else a_total = w_init;
+  stats.kernel_launches += apply_device(a_total.data(), mean.empty() ? nullptr : mean.data(), nc, nf, d_x, ldx, x1.p, ld1, t_local,
+                                        guard.sm_count, st);
+  PICARD_CUDA(cudaEventRecord(e1, st));
+  PICARD_CUDA(cudaStreamSynchronize(st));
+  float pre_ms = 0.f;
+  PICARD_CUDA(cudaEventElapsedTime(&pre_ms, e0, e1));
+  stats.preprocess_ms = pre_ms;
+
+  if (cfg.verbose && (!cfg.comm || comm_rank(cfg.comm) == 0)) printf("Running Picard...\n");
+  CoreSolver core(x1.p, nc, t_local, ld1, cfg, extended && cfg.whiten, guard.sm_count, st);  // solver.rs:143-166
+  core.run(cfg.max_iter);
+  std::vector<double> wc((size_t)nc * nc), signs((size_t)nc);
+  core.state(wc.data(), signs.data(), nullptr, nullptr, nullptr, nullptr);
+  std::vector<double> wfull((size_t)nc * nc);
+  host_matmul(wc.data(), w_init.data(), wfull.data(), nc, nc, nc);            // solver.rs:169
+  if (!core.converged() && cfg.verbose && (!cfg.comm || comm_rank(cfg.comm) == 0))
+    fprintf(stderr, "Warning: PICARD did not converge. Final gradient norm: %.4e, tolerance: %.4e\n", core.gradient_norm(), cfg.tol);
+
+  // sources = Y = W_core x1 (the reference returns the Y the norm was measured at: quirk Q10)
+  const picard_stats_t& cs = core.stats();
+  stats.core_ms = cs.core_ms; stats.fused_passes = cs.fused_passes; stats.grad_passes = cs.grad_passes; stats.loss_passes = cs.loss_passes;
+  stats.ls_tries = cs.ls_tries; stats.fallbacks = cs.fallbacks; stats.sign_changes = cs.sign_changes;
+  stats.kernel_launches += cs.kernel_launches;
+  stats.pass_ms_fused = cs.pass_ms_fused; stats.pass_ms_grad = cs.pass_ms_grad; stats.pass_ms_loss = cs.pass_ms_loss;
+  const bool keep_dev = (cfg.flags & PICARD_FLAG_KEEP_SOURCES_ON_DEVICE) != 0;
+  double* host_sources = nullptr;
+  if (d_sources) {
+    stats.kernel_launches += apply_device(wc.data(), nullptr, nc, nc, x1.p, ld1, d_sources, lds, t_local, guard.sm_count, st);
+    if (!keep_dev) {
+      host_sources = (double*)malloc(sizeof(double) * (size_t)nc * t_local);
+      if (!host_sources) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: out of host memory");
+      PICARD_CUDA(cudaMemcpy2DAsync(host_sources, sizeof(double) * t_local, d_sources, sizeof(double) * lds, sizeof(double) * t_local, nc,
+                                    cudaMemcpyDeviceToHost, st));
+      PICARD_CUDA(cudaStreamSynchronize(st));
+      stats.d2h_bytes += (int64_t)sizeof(double) * nc * t_local;
+    }
+  } else if (!keep_dev) {
+    DevBuf<double> ysrc((size_t)nc * ld1);
+    stats.kernel_launches += apply_device(wc.data(), nullptr, nc, nc, x1.p, ld1, ysrc.p, ld1, t_local, guard.sm_count, st);
+    host_sources = (double*)malloc(sizeof(double) * (size_t)nc * t_local);
+    if (!host_sources) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: out of host memory");
+    cudaEvent_t d0, d1;
+    PICARD_CUDA(cudaEventCreate(&d0)); PICARD_CUDA(cudaEventCreate(&d1));
+    PICARD_CUDA(cudaEventRecord(d0, st));
+    PICARD_CUDA(cudaMemcpy2DAsync(host_sources, sizeof(double) * t_local, ysrc.p, sizeof(double) * ld1, sizeof(double) * t_local, nc,
+                                  cudaMemcpyDeviceToHost, st));
+    PICARD_CUDA(cudaEventRecord(d1, st));
+    PICARD_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f; cudaEventElapsedTime(&ms, d0, d1); stats.d2h_ms += ms;
+    cudaEventDestroy(d0); cudaEventDestroy(d1);
+    stats.d2h_bytes += (int64_t)sizeof(double) * nc * t_local;
+  }
+
+  out->n_components = nc; out->n_features = nf; out->n_samples = t_local;
+  out->whitening = cfg.whiten ? dup_host(K.data(), K.size()) : nullptr;
+  out->unmixing = dup_host(wfull.data(), wfull.size());
+  out->sources = host_sources;
+  out->mean = mean.empty() ? nullptr : dup_host(mean.data(), mean.size());
+  out->n_iterations = core.n_iterations(); out->converged = core.converged() ? 1 : 0; out->gradient_norm = core.gradient_norm();
+  out->signs = core.extended() ? dup_host(signs.data(), signs.size()) : nullptr;
+  out->stats = stats;
+}
+
+void fit_host(const double* x, int64_t n_features, int64_t n_samples, int64_t row_stride, const picard_config_t& cfg,
+              picard_result_t* out) {
+  memset(out, 0, sizeof *out);
+  config_validate(cfg);
+  if (n_features <= 0 || n_samples <= 0 || x == nullptr)
+    throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
+  DeviceGuard guard(cfg.device);
+  const int64_t ldx = round_up(n_samples, 16);
+  DevBuf<double> dx((size_t)n_features * ldx);
+  cudaEvent_t e0, e1;
+  PICARD_CUDA(cudaEventCreate(&e0)); PICARD_CUDA(cudaEventCreate(&e1));
+  PICARD_CUDA(cudaEventRecord(e0, 0));
+  PICARD_CUDA(cudaMemcpy2DAsync(dx.p, sizeof(double) * ldx, x, sizeof(double) * row_stride, sizeof(double) * n_samples, n_features,
+                                cudaMemcpyHostToDevice, 0));
+  PICARD_CUDA(cudaEventRecord(e1, 0));
+  PICARD_CUDA(cudaStreamSynchronize(0));
+  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  picard_config_t c2 = cfg;
+  c2.device = guard.device;
+  c2.flags &= ~PICARD_FLAG_KEEP_SOURCES_ON_DEVICE;
+  fit_device(dx.p, n_features, n_samples, ldx, c2, nullptr, 0, out);
+  out->stats.h2d_ms += ms;
+  out->stats.h2d_bytes += (int64_t)sizeof(double) * n_features * n_samples;
+}
+
+void transform_host(const double* x, int64_t n_features, int64_t n_samples, int64_t row_stride, const picard_result_t& res,
+                    double* out, int device) {
+  if (n_features <= 0 || n_samples <= 0) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
+  if (n_features != res.n_features)
+    throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: transform input has " + std::to_string(n_features) +
+                                               " features, the model was fitted on " + std::to_string(res.n_features));
+  DeviceGuard guard(device);
+  const int nc = (int)res.n_components, nf = (int)res.n_features;
+  std::vector<double> wfull((size_t)nc * nf);
+  if (res.whitening) host_matmul(res.unmixing, res.whitening, wfull.data(), nc, nc, nf);  // result.rs:39-44
+  else memcpy(wfull.data(), res.unmixing, sizeof(double) * nc * nc);
+  const int64_t ldx = round_up(n_samples, 16);
+  DevBuf<double> dx((size_t)nf * ldx), dy((size_t)nc * ldx);
+  PICARD_CUDA(cudaMemcpy2DAsync(dx.p, sizeof(double) * ldx, x, sizeof(double) * row_stride, sizeof(double) * n_samples, nf,
+                                cudaMemcpyHostToDevice, 0));
+  apply_device(wfull.data(), res.mean, nc, nf, dx.p, ldx, dy.p, ldx, n_samples, guard.sm_count, 0);
+  PICARD_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * n_samples, dy.p, sizeof(double) * ldx, sizeof(double) * n_samples, nc,
+                                cudaMemcpyDeviceToHost, 0));
+  PICARD_CUDA(cudaStreamSynchronize(0));
+}
+
+}  // namespace picard

@@ -1,0 +1,2 @@
+#include "pass_inst.cuh"
+namespace picard { template int launch_pass_np<128>(const PassLaunch&, const CUtensorMap&); }

@@ -1,0 +1,685 @@
+// N x N device kernels of the core loop.  See small.cuh.  Reference citations per kernel.
+#include "small.cuh"
+
+#include <cmath>
+
+#include "pass.cuh"  // moment-buffer layout helpers
+
+namespace picard {
+namespace small {
+
+namespace {
+
+constexpr int BT1 = 1024;  // single-CTA kernels
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double r = lane < nw ? sh[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (lane == 0) sh[32] = r;
+  }
+  __syncthreads();
+  double r = sh[32];
+  __syncthreads();
+  return r;
+}
+// fmax ignores NaN operands like Rust's f64::max in `fold(0.0, f64::max)` (core.rs:289, math.rs:42)
+__device__ __forceinline__ double block_max(double v, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double r = lane < nw ? sh[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if (lane == 0) sh[32] = r;
+  }
+  __syncthreads();
+  double r = sh[32];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double rust_signum(double v) {  // quirk Q8: +0 -> +1, -0 -> -1, NaN -> NaN
+  if (v != v) return v;
+  return signbit(v) ? -1.0 : 1.0;
+}
+
+// loss from reduced moments: core.rs:51-82 after the per-row sums
+__device__ double loss_of_point(const CoreDims& d, const double* mom, const double* signs, bool* singular) {
+  const int n = d.n;
+  const double tf = d.t_total;
+  double loss = 0.0;
+  *singular = false;
+  if (!d.ortho) {
+    const double* ex = mom + mom_size(n);
+    if (ex[1] == 0.0) { *singular = true; return 1e15; }
+    loss = -ex[0];
+  }
+  const double* L = mom + mom_off_ll(n);
+  const double* Sq = mom + mom_off_sq(n);
+  for (int i = 0; i < n; ++i) {
+    const double s = signs ? signs[i] : 1.0;
+    loss += s * L[i] / tf;
+    if (d.extended && !d.ortho) loss += 0.5 * Sq[i] / tf;
+  }
+  return loss;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// iteration front + L-BFGS update + direction, single CTA
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT1) front_kernel(FrontArgs a) {
+  __shared__ double sh[33];
+  __shared__ int sh_flag;
+  const int n = a.d.n, nn = n * n, tid = threadIdx.x, nt = blockDim.x;
+  const double tf = a.d.t_total;
+  const bool ortho = a.d.ortho != 0, ext = a.d.extended != 0;
+  const double* Gr = a.mom + mom_off_gr(n);
+  const double* Hr = a.mom + mom_off_hr(n);
+  const double* Sd = a.mom + mom_off_sd(n);
+  const double* Sq = a.mom + mom_off_sq(n);
+
+  const int m = a.d.m;
+  int len = 0, head = 0;
+  if (a.do_lbfgs != 2) {
+  if (tid == 0) sh_flag = 0;
+  __syncthreads();
+  // ---- extended: kurtosis-sign estimate (core.rs:225-237)
+  if (ext) {
+    int change = 0;
+    for (int i = tid; i < n; i += nt) {
+      const double pm = Sd[i] / tf, gii = Gr[i * n + i] / tf;
+      const double s = rust_signum(pm * a.C[i * n + i] - gii);
+      if (!a.first_iter && s != a.old_signs[i]) change = 1;
+      a.signs[i] = s;
+      a.old_signs[i] = s;
+    }
+    if (change) atomicOr(&sh_flag, 1);
+  } else {
+    for (int i = tid; i < n; i += nt) a.signs[i] = 1.0;
+  }
+  __syncthreads();
+  const int sign_change = sh_flag;
+  // ---- g = Gr / T, sign-scaled rows, + C when not ortho (core.rs:218, 240-252)
+  for (int e = tid; e < nn; e += nt) {
+    const int i = e / n;
+    double v = Gr[e] / tf;
+    if (ext) {
+      v *= a.signs[i];
+      if (!ortho) v = v + a.C[e];
+    }
+    a.Gtmp[e] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) a.hoff[i] = ortho ? a.Gtmp[i * n + i] : 1.0;  // core.rs:256-260
+  __syncthreads();
+  // ---- Hessian approximation (core.rs:263-277)
+  if (ortho) {
+    for (int e = tid; e < nn; e += nt) {
+      const int i = e / n, j = e % n;
+      const double pmi = (ext ? a.signs[i] : 1.0) * (Sd[i] / tf), pmj = (ext ? a.signs[j] : 1.0) * (Sd[j] / tf);
+      a.H[e] = fmax(0.5 * (pmi + pmj - a.hoff[i] - a.hoff[j]), a.d.lambda_min);
+    }
+  } else {
+    for (int e = tid; e < nn; e += nt) {
+      const int i = e / n, j = e % n;
+      a.H[e] = ext ? (a.signs[i] * Hr[e] + Sq[j]) / tf : Hr[e] / tf;
+    }
+    __syncthreads();
+    // regularize_hessian (lbfgs.rs:155-171): sequential in-place semantics = per unordered pair, (i,j) then (j,i)
+    const int npairs = n * (n - 1) / 2;
+    for (int pidx = tid; pidx < npairs; pidx += nt) {
+      // unrank (i < j)
+      int i = (int)((2.0 * n - 1.0 - sqrt((2.0 * n - 1.0) * (2.0 * n - 1.0) - 8.0 * pidx)) * 0.5);
+      while ((long long)i * (2 * n - i - 1) / 2 > pidx) --i;
+      while ((long long)(i + 1) * (2 * n - i - 2) / 2 <= pidx) ++i;
+      const int j = pidx - (int)((long long)i * (2 * n - i - 1) / 2) + i + 1;
+      double hij = a.H[i * n + j], hji = a.H[j * n + i];
+      const double four = 4.0 * a.hoff[i] * a.hoff[j];
+      {
+        const double diff = hij - hji, discr = sqrt(diff * diff + four), ev = 0.5 * (hij + hji - discr);
+        if (ev < a.d.lambda_min) hij += a.d.lambda_min - ev;
+      }
+      {
+        const double diff = hji - hij, discr = sqrt(diff * diff + four), ev = 0.5 * (hji + hij - discr);
+        if (ev < a.d.lambda_min) hji += a.d.lambda_min - ev;
+      }
+      a.H[i * n + j] = hij;
+      a.H[j * n + i] = hji;
+    }
+  }
+  // ---- projection (core.rs:280-286) and norm (core.rs:289)
+  double mx = 0.0;
+  for (int e = tid; e < nn; e += nt) {
+    const int i = e / n, j = e % n;
+    double v;
+    if (ortho) v = (a.Gtmp[e] - a.Gtmp[j * n + i]) / 2.0;
+    else v = (i == j) ? a.Gtmp[e] - 1.0 : a.Gtmp[e];
+    a.G[e] = v;
+    mx = fmax(mx, fabs(v));
+  }
+  const double gnorm = block_max(mx, sh);
+  if (tid == 0) {
+    a.sc->gradient_norm = gnorm;
+    a.sc->sign_change = sign_change;
+  }
+  if (!a.do_lbfgs) return;
+  __syncthreads();
+
+  // ---- L-BFGS memory update (core.rs:296-314, quirk Q9)
+  len = a.sc->mem_len; head = a.sc->mem_head;
+  const int have_prev = a.sc->have_prev_step, have_old = a.sc->have_g_old;
+  __syncthreads();
+  if (!a.first_iter && have_prev && have_old) {
+    double part = 0.0;
+    for (int e = tid; e < nn; e += nt) {
+      const double yd = a.G[e] - a.G_old[e];
+      a.q[e] = yd;
+      part += a.S_prev[e] * yd;
+    }
+    const double dot = block_sum(part, sh);
+    const double r = 1.0 / dot;
+    if (isfinite(r)) {
+      int slot;
+      if (len < m) { slot = (head + len) % m; ++len; }
+      else { slot = head; head = (head + 1) % m; }
+      for (int e = tid; e < nn; e += nt) {
+        a.mem_s[(size_t)slot * nn + e] = a.S_prev[e];
+        a.mem_y[(size_t)slot * nn + e] = a.q[e];
+      }
+      if (tid == 0) a.mem_r[slot] = r;
+    }
+    if (tid == 0) { a.sc->have_prev_step = 0; a.sc->last_r = r; }
+  }
+  for (int e = tid; e < nn; e += nt) a.G_old[e] = a.G[e];
+  // ---- sign change: loss with the new signs, flush memory (core.rs:317-331, quirk Q11)
+  if (ext && sign_change) {
+    if (tid == 0) {
+      bool sing;
+      const double l = loss_of_point(a.d, a.mom, a.signs, &sing);
+      a.sc->current_loss = l;  // singular -> 1e15 and continue
+    }
+    len = 0; head = 0;
+  }
+  if (tid == 0) { a.sc->mem_len = len; a.sc->mem_head = head; a.sc->have_g_old = 1; }
+  __syncthreads();
+
+  } else {
+    len = a.sc->mem_len; head = a.sc->mem_head;
+    __syncthreads();
+  }
+  // ---- direction: two-loop recursion (lbfgs.rs:84-133)
+  double* alist = a.mem_r + m;
+  for (int e = tid; e < nn; e += nt) a.q[e] = a.G[e];
+  __syncthreads();
+  for (int k = len - 1; k >= 0; --k) {
+    const int slot = (head + k) % m;
+    const double* s = a.mem_s + (size_t)slot * nn;
+    const double* y = a.mem_y + (size_t)slot * nn;
+    double part = 0.0;
+    for (int e = tid; e < nn; e += nt) part += s[e] * a.q[e];
+    const double al = a.mem_r[slot] * block_sum(part, sh);
+    if (tid == 0) alist[k] = al;
+    for (int e = tid; e < nn; e += nt) a.q[e] = a.q[e] - al * y[e];
+    __syncthreads();
+  }
+  // preconditioner
+  if (ortho) {
+    for (int e = tid; e < nn; e += nt) a.Gtmp[e] = a.q[e] / a.H[e];
+    __syncthreads();
+    for (int e = tid; e < nn; e += nt) {
+      const int i = e / n, j = e % n;
+      a.D[e] = (a.Gtmp[e] - a.Gtmp[j * n + i]) / 2.0;
+    }
+  } else {  // solve_hessian_system (lbfgs.rs:136-150, quirk Q15)
+    for (int e = tid; e < nn; e += nt) {
+      const int i = e / n, j = e % n, et = j * n + i;
+      const double det = a.H[e] * a.H[et] - a.hoff[i] * a.hoff[j];
+      double v = 0.0;
+      if (fabs(det) > 1e-15) v = (a.H[et] * a.q[e] - a.hoff[i] * a.q[et]) / det;
+      a.D[e] = v;
+    }
+  }
+  __syncthreads();
+  for (int k = 0; k < len; ++k) {
+    const int slot = (head + k) % m;
+    const double* s = a.mem_s + (size_t)slot * nn;
+    const double* y = a.mem_y + (size_t)slot * nn;
+    double part = 0.0;
+    for (int e = tid; e < nn; e += nt) part += y[e] * a.D[e];
+    const double beta = a.mem_r[slot] * block_sum(part, sh);
+    const double cf = alist[k] - beta;
+    for (int e = tid; e < nn; e += nt) a.D[e] = a.D[e] + cf * s[e];
+    __syncthreads();
+  }
+  double dm = 0.0;
+  for (int e = tid; e < nn; e += nt) {
+    const double v = -a.D[e];
+    a.D[e] = v;
+    dm = fmax(dm, fabs(v));
+  }
+  const double nd = block_max(dm, sh);
+  if (tid == 0) a.sc->norm_d = nd;
+}
+
+__global__ void loss_kernel(CoreDims d, const double* mom, const double* signs, CoreScalars* sc, int which) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  bool sing;
+  const double l = loss_of_point(d, mom, signs, &sing);
+  if (which == 0) {
+    sc->new_loss = l;
+    sc->accept = (l < sc->current_loss) ? 1 : 0;
+  } else {
+    sc->current_loss = l;
+    sc->loss_singular = sing ? 1 : 0;
+  }
+}
+
+__global__ void accept_kernel(const double* D, double alpha, double* S_prev, int64_t count, CoreScalars* sc) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x)
+    S_prev[e] = D[e] * alpha;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->current_loss = sc->new_loss;
+    sc->have_prev_step = 1;
+  }
+}
+__global__ void negate_kernel(const double* G, double* D, int64_t count, CoreScalars* sc) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) D[e] = -G[e];
+  if (blockIdx.x == 0 && threadIdx.x == 0) { sc->mem_len = 0; sc->mem_head = 0; sc->norm_d = sc->gradient_norm; }
+}
+__global__ void clear_memory_kernel(CoreScalars* sc) { sc->mem_len = 0; sc->mem_head = 0; }
+__global__ void scale_kernel(const double* A, double* B, int64_t count, double alpha) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) B[e] = A[e] * alpha;
+}
+__global__ void eye_plus_kernel(const double* D, double alpha, double* M, int n) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x)
+    M[e] = ((e / n == e % n) ? 1.0 : 0.0) + alpha * D[e];
+}
+__global__ void identity_kernel(double* A, int n) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) A[e] = (e / n == e % n) ? 1.0 : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small dense matmul: 32 x 32 output tile per CTA of 256 threads (2 x 2 per thread), k in chunks of 32
+// ---------------------------------------------------------------------------------------------------
+template <bool TRANS_B>
+__device__ __forceinline__ void tile_mm(const double* A, int lda, const double* B, int ldb, int m, int k, int n, int bi, int bj,
+                                        double acc[2][2]) {
+  __shared__ double As[32][33], Bs[32][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.0;
+  for (int k0 = 0; k0 < k; k0 += 32) {
+    for (int e = threadIdx.x; e < 1024; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      const int gi = bi * 32 + r, gk = k0 + c;
+      As[r][c] = (gi < m && gk < k) ? A[(size_t)gi * lda + gk] : 0.0;
+      const int gkk = k0 + r, gj = bj * 32 + c;
+      double bv = 0.0;
+      if (gkk < k && gj < n) bv = TRANS_B ? B[(size_t)gj * ldb + gkk] : B[(size_t)gkk * ldb + gj];
+      Bs[r][c] = bv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const double a0 = As[ty][kk], a1 = As[ty + 16][kk], b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
+      acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
+      acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+}
+
+template <bool TRANS_B>
+__global__ void __launch_bounds__(256) matmul_kernel(const double* A, const double* B, double* C, int m, int k, int n, double alpha,
+                                                     int add_identity) {
+  double acc[2][2];
+  tile_mm<TRANS_B>(A, k, B, TRANS_B ? k : n, m, k, n, blockIdx.y, blockIdx.x, acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int i = blockIdx.y * 32 + ty + 16 * a, j = blockIdx.x * 32 + tx + 16 * b;
+      if (i < m && j < n) {
+        double v = alpha * acc[a][b];
+        if (add_identity && i == j) v += 1.0;
+        C[(size_t)i * n + j] = v;
+      }
+    }
+}
+
+// one Taylor term of matrix_exp (math.rs:58-66): term_k = term_{k-1} A / k ; result += term_k ;
+// slots[k] = max |term_k| ; skipped entirely once a previous term fell below 1e-16 (the `break`).
+__global__ void __launch_bounds__(256) expm_term_kernel(const double* term_prev, const double* As, double* term_new, double* result,
+                                                        double* slots, int n, int k) {
+  if (slots[k - 1] < 1e-16) return;  // uniform across the grid: slots[k-1] was finalised by the previous launch
+  double acc[2][2];
+  tile_mm<false>(term_prev, n, As, n, n, n, n, blockIdx.y, blockIdx.x, acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double mx = 0.0;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int i = blockIdx.y * 32 + ty + 16 * a, j = blockIdx.x * 32 + tx + 16 * b;
+      if (i < n && j < n) {
+        const double v = acc[a][b] / (double)k;
+        term_new[(size_t)i * n + j] = v;
+        result[(size_t)i * n + j] += v;
+        mx = fmax(mx, fabs(v));
+      }
+    }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(&slots[k]), (unsigned long long)__double_as_longlong(mx));
+}
+// A_s = D * alpha / scale ; term_1 = A_s ; result = I + A_s ; slots[0] = 1, slots[1] = max|A_s|, others 0
+__global__ void expm_prepare_kernel(const double* D, double alpha, double scale, int n, double* As, double* term, double* result,
+                                    double* slots) {
+  __shared__ double sh[33];
+  double mx = 0.0;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const double v = (D[e] * alpha) / scale;
+    As[e] = v; term[e] = v;
+    result[e] = ((e / n == e % n) ? 1.0 : 0.0) + v;
+    mx = fmax(mx, fabs(v));
+  }
+  mx = block_max(mx, sh);
+  if (threadIdx.x < 32) slots[threadIdx.x] = threadIdx.x == 0 ? 1.0 : (threadIdx.x == 1 ? mx : 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// signed log-determinant: LU with partial pivoting, single CTA, in `work` (n x n)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT1) lu_logdet_kernel(const double* A, int n, double* work, double* out2) {
+  __shared__ double shv[32];
+  __shared__ int shi[32];
+  __shared__ int piv_row;
+  __shared__ double piv_val;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (int e = tid; e < n * n; e += nt) work[e] = A[e];
+  __syncthreads();
+  double logabs = 0.0, sign = 1.0;
+  for (int k = 0; k < n; ++k) {
+    double bv = -1.0; int bi = n;
+    for (int i = k + tid; i < n; i += nt) {
+      const double v = fabs(work[(size_t)i * n + k]);
+      if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { shv[warp] = bv; shi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double v = shv[0]; int idx = shi[0];
+      for (int w = 1; w < nw; ++w) if (shv[w] > v || (shv[w] == v && shi[w] < idx)) { v = shv[w]; idx = shi[w]; }
+      piv_row = idx; piv_val = v;
+    }
+    __syncthreads();
+    const int p = piv_row;
+    if (!(piv_val > 0.0)) { sign = 0.0; break; }  // exactly singular (or NaN column)
+    if (p != k) {
+      for (int j = tid; j < n; j += nt) {
+        const double t = work[(size_t)k * n + j];
+        work[(size_t)k * n + j] = work[(size_t)p * n + j];
+        work[(size_t)p * n + j] = t;
+      }
+      sign = -sign;
+    }
+    __syncthreads();
+    const double d = work[(size_t)k * n + k];
+    if (d < 0.0) sign = -sign;
+    logabs += log(fabs(d));
+    const int rem = n - k - 1;
+    for (int e = tid; e < rem * rem; e += nt) {
+      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+      work[(size_t)i * n + j] -= (work[(size_t)i * n + k] / d) * work[(size_t)k * n + j];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (sign == 0.0) { out2[0] = -INFINITY; out2[1] = 0.0; }
+    else { out2[0] = logabs; out2[1] = sign; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cyclic Jacobi eigensolver, single CTA, round-robin parallel ordering
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT1) jacobi_kernel(double* A, int n, double* V, double* evals, double* tmp) {
+  __shared__ double sh[33];
+  __shared__ double cs_c[256], cs_s[256];
+  __shared__ int pr_p[256], pr_q[256];
+  __shared__ int order[512];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int np = n + (n & 1);  // players (one dummy if n is odd)
+  const int half = np / 2;
+  for (int e = tid; e < n * n; e += nt) V[e] = (e / n == e % n) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int e = tid; e < n * n; e += nt) {
+      const double v = A[e];
+      if (e / n == e % n) dg += v * v; else off += v * v;
+    }
+    off = block_sum(off, sh);
+    dg = block_sum(dg, sh);
+    if (off <= 1e-32 * dg || off == 0.0) break;
+    for (int r = 0; r < np - 1; ++r) {
+      if (tid < half) {
+        int p, q;
+        if (tid == 0) { p = np - 1; q = r; }
+        else { p = (r + tid) % (np - 1); q = (r - tid + (np - 1)) % (np - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, s = 0.0;
+        if (q < n) {
+          const double apq = A[(size_t)p * n + q];
+          if (apq != 0.0) {
+            const double app = A[(size_t)p * n + p], aqq = A[(size_t)q * n + q];
+            const double tau = (aqq - app) / (2.0 * apq);
+            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = t * c;
+          }
+        } else { q = -1; }
+        pr_p[tid] = p; pr_q[tid] = q; cs_c[tid] = c; cs_s[tid] = s;
+      }
+      __syncthreads();
+      for (int e = tid; e < half * n; e += nt) {  // rows: A <- J^T A
+        const int pr = e / n, jj = e % n, p = pr_p[pr], q = pr_q[pr];
+        if (q < 0) continue;
+        const double c = cs_c[pr], s = cs_s[pr];
+        const double ap = A[(size_t)p * n + jj], aq = A[(size_t)q * n + jj];
+        A[(size_t)p * n + jj] = c * ap - s * aq;
+        A[(size_t)q * n + jj] = s * ap + c * aq;
+      }
+      __syncthreads();
+      for (int e = tid; e < half * n; e += nt) {  // columns: A <- A J, V <- V J
+        const int pr = e % half, i = e / half, p = pr_p[pr], q = pr_q[pr];
+        if (q < 0) continue;
+        const double c = cs_c[pr], s = cs_s[pr];
+        const double ap = A[(size_t)i * n + p], aq = A[(size_t)i * n + q];
+        A[(size_t)i * n + p] = c * ap - s * aq;
+        A[(size_t)i * n + q] = s * ap + c * aq;
+        const double vp = V[(size_t)i * n + p], vq = V[(size_t)i * n + q];
+        V[(size_t)i * n + p] = c * vp - s * vq;
+        V[(size_t)i * n + q] = s * vp + c * vq;
+      }
+      __syncthreads();
+    }
+  }
+  // ascending order of the diagonal
+  if (tid == 0) {
+    for (int i = 0; i < n; ++i) order[i] = i;
+    for (int i = 1; i < n; ++i) {
+      const int o = order[i]; const double v = A[(size_t)o * n + o];
+      int k = i - 1;
+      while (k >= 0 && A[(size_t)order[k] * n + order[k]] > v) { order[k + 1] = order[k]; --k; }
+      order[k + 1] = o;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) evals[i] = A[(size_t)order[i] * n + order[i]];
+  for (int e = tid; e < n * n; e += nt) tmp[e] = V[(size_t)(e / n) * n + order[e % n]];
+  __syncthreads();
+  for (int e = tid; e < n * n; e += nt) V[e] = tmp[e];
+}
+
+__global__ void symdecor_scale_kernel(const double* U, const double* evals, int n, double* scaled, int* status) {
+  __shared__ double sh[33];
+  double mn = INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mn = fmin(mn, evals[i]);
+  mn = -block_max(-mn, sh);
+  if (threadIdx.x == 0) *status = (mn < 1e-10) ? PICARD_SINGULAR_MATRIX : PICARD_OK;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) scaled[e] = U[e] * (1.0 / sqrt(evals[e % n]));
+}
+
+inline int ew_blocks(int64_t count) { int64_t b = (count + 255) / 256; return (int)(b > 1184 ? 1184 : (b < 1 ? 1 : b)); }
+
+}  // namespace
+
+#define LAUNCH_CHECK() PICARD_CUDA(cudaGetLastError())
+
+int matmul(const double* A, const double* B, double* C, int n, bool trans_b, double alpha, bool add_identity, cudaStream_t st) {
+  dim3 grid((n + 31) / 32, (n + 31) / 32);
+  if (trans_b) matmul_kernel<true><<<grid, 256, 0, st>>>(A, B, C, n, n, n, alpha, add_identity ? 1 : 0);
+  else matmul_kernel<false><<<grid, 256, 0, st>>>(A, B, C, n, n, n, alpha, add_identity ? 1 : 0);
+  LAUNCH_CHECK();
+  return 1;
+}
+int matmul_rect(const double* A, const double* B, double* C, int m, int k, int n, cudaStream_t st) {
+  dim3 grid((n + 31) / 32, (m + 31) / 32);
+  matmul_kernel<false><<<grid, 256, 0, st>>>(A, B, C, m, k, n, 1.0, 0);
+  LAUNCH_CHECK();
+  return 1;
+}
+int set_identity(double* A, int n, cudaStream_t st) {
+  identity_kernel<<<ew_blocks((int64_t)n * n), 256, 0, st>>>(A, n);
+  LAUNCH_CHECK();
+  return 1;
+}
+int eye_plus_scaled(const double* D, double alpha, double* M, int n, cudaStream_t st) {
+  eye_plus_kernel<<<ew_blocks((int64_t)n * n), 256, 0, st>>>(D, alpha, M, n);
+  LAUNCH_CHECK();
+  return 1;
+}
+int copy_scaled(const double* A, double* B, int64_t count, double alpha, cudaStream_t st) {
+  scale_kernel<<<ew_blocks(count), 256, 0, st>>>(A, B, count, alpha);
+  LAUNCH_CHECK();
+  return 1;
+}
+int iteration_front(const FrontArgs& a, cudaStream_t st) {
+  const int nn = a.d.n * a.d.n;
+  int threads = nn >= 1024 ? 1024 : ((nn + 31) / 32) * 32;
+  if (threads < 32) threads = 32;
+  front_kernel<<<1, threads, 0, st>>>(a);
+  LAUNCH_CHECK();
+  return 1;
+}
+int loss_from_moments(const CoreDims& d, const double* mom, const double* signs, CoreScalars* sc, int which, cudaStream_t st) {
+  loss_kernel<<<1, 32, 0, st>>>(d, mom, signs, sc, which);
+  LAUNCH_CHECK();
+  return 1;
+}
+int accept_step(const CoreDims& d, const double* D, double alpha, double* S_prev, const double* W, double* C, int update_c,
+                CoreScalars* sc, cudaStream_t st) {
+  const int64_t nn = (int64_t)d.n * d.n;
+  accept_kernel<<<ew_blocks(nn), 256, 0, st>>>(D, alpha, S_prev, nn, sc);
+  LAUNCH_CHECK();
+  int launches = 1;
+  if (update_c) launches += matmul(W, W, C, d.n, true, 1.0, false, st);
+  return launches;
+}
+int negate_into(const double* G, double* D, int64_t count, CoreScalars* sc, cudaStream_t st) {
+  negate_kernel<<<ew_blocks(count), 256, 0, st>>>(G, D, count, sc);
+  LAUNCH_CHECK();
+  return 1;
+}
+int clear_memory(CoreScalars* sc, cudaStream_t st) {
+  clear_memory_kernel<<<1, 1, 0, st>>>(sc);
+  LAUNCH_CHECK();
+  return 1;
+}
+
+int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWork& w, double* out, cudaStream_t st) {
+  const double norm = norm_d * alpha;  // max |D * alpha| (alpha > 0)
+  int launches = 0;
+  if (!(norm >= 1e-15)) {  // math.rs:43-45 (NaN norms cannot occur: fmax ignores NaN entries)
+    return set_identity(out, n, st);
+  }
+  const int s = (int)std::fmax(std::ceil(std::log2(norm)), 0.0);
+  const double scale = std::ldexp(1.0, s);
+  int threads = n * n >= 1024 ? 1024 : ((n * n + 31) / 32) * 32;
+  double* res = (s == 0) ? out : w.res0;
+  expm_prepare_kernel<<<1, threads, 0, st>>>(D, alpha, scale, n, w.As, w.term1, res, w.slots);
+  LAUNCH_CHECK();
+  ++launches;
+  dim3 grid((n + 31) / 32, (n + 31) / 32);
+  for (int k = 2; k <= 30; ++k) {
+    const double* tp = (k & 1) ? w.term0 : w.term1;  // term_{k-1}: term_1 lives in term1
+    double* tn = (k & 1) ? w.term1 : w.term0;
+    expm_term_kernel<<<grid, 256, 0, st>>>(tp, w.As, tn, res, w.slots, n, k);
+    LAUNCH_CHECK();
+    ++launches;
+  }
+  // squaring (math.rs:69-71)
+  double* cur = res;
+  for (int i = 0; i < s; ++i) {
+    double* nxt = (i == s - 1) ? out : (cur == w.res0 ? w.res1 : w.res0);
+    launches += matmul(cur, cur, nxt, n, false, 1.0, false, st);
+    cur = nxt;
+  }
+  return launches;
+}
+
+int sln_det(const double* A, int n, double* work, double* out2, cudaStream_t st) {
+  int threads = n >= 48 ? 1024 : 256;
+  lu_logdet_kernel<<<1, threads, 0, st>>>(A, n, work, out2);
+  LAUNCH_CHECK();
+  return 1;
+}
+
+int jacobi_eigh(double* A, int n, double* V, double* evals, cudaStream_t st) {
+  if (n > 512) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: eigendecomposition supports n <= 512");
+  // tmp for the final column permutation: reuse the tail of the caller's buffers is error-prone; allocate async
+  double* tmp = nullptr;
+  PICARD_CUDA(cudaMallocAsync(&tmp, sizeof(double) * (size_t)n * n, st));
+  int threads = n * n >= 1024 ? 1024 : ((n * n + 31) / 32) * 32;
+  if (threads < 32) threads = 32;
+  jacobi_kernel<<<1, threads, 0, st>>>(A, n, V, evals, tmp);
+  LAUNCH_CHECK();
+  PICARD_CUDA(cudaFreeAsync(tmp, st));
+  return 1;
+}
+
+int sym_decorrelation(const double* W, int n, double* work, double* out, int* status_dev, cudaStream_t st) {
+  double* wwt = work;
+  double* U = work + (size_t)n * n;
+  double* scaled = work + 2 * (size_t)n * n;
+  double* t2 = work + 3 * (size_t)n * n;
+  double* ev = work + 4 * (size_t)n * n;
+  int launches = matmul(W, W, wwt, n, true, 1.0, false, st);
+  launches += jacobi_eigh(wwt, n, U, ev, st);
+  int threads = n * n >= 1024 ? 1024 : ((n * n + 31) / 32) * 32;
+  symdecor_scale_kernel<<<1, threads, 0, st>>>(U, ev, n, scaled, status_dev);
+  LAUNCH_CHECK();
+  ++launches;
+  launches += matmul(scaled, U, t2, n, true, 1.0, false, st);
+  launches += matmul(t2, W, out, n, false, 1.0, false, st);
+  return launches;
+}
+
+}  // namespace small
+}  // namespace picard

@@ -173,6 +173,12 @@ int picard_compute_direction(const double* g, const double* h, const double* hof
 int picard_center_whiten(const double* x, int64_t n_features, int64_t n_samples, int64_t row_stride, int64_t n_components,
                          int32_t centering, int32_t device, double* mean, double* k, double* data, char* err,
                          size_t errlen);
+/* Same for a DEVICE-resident sample matrix (this rank's column shard when comm != NULL): mean (nf, host) and
+ * k (nc x nf, host) only; the caller applies them with picard_apply_device.  What bench.py uses to prepare the
+ * core loop's input without a host round trip. */
+int picard_center_whiten_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_t row_stride,
+                                int64_t n_components, int32_t centering, picard_comm_t* comm, int32_t device, double* mean,
+                                double* k, char* err, size_t errlen);
 /* jade.rs:22-72 on the device: x whitened (n x n_samples) host; w (n x n) out. */
 int picard_jade(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, int64_t max_iter, double tol,
                 int32_t verbose, int32_t device, double* w, int64_t* sweeps, char* err, size_t errlen);

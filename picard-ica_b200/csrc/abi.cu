@@ -324,6 +324,33 @@ int picard_center_whiten(const double* x, int64_t n_features, int64_t n_samples,
   });
 }
 
+int picard_center_whiten_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_t row_stride, int64_t n_components,
+                                int32_t centering, picard_comm_t* comm, int32_t device, double* mean, double* k, char* err,
+                                size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (n_features <= 0 || n_samples <= 0 || !d_x) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
+    DeviceGuard guard(device);
+    cudaStream_t st;
+    PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
+    double t_total = (double)n_samples;
+    if (comm && comm_size(comm) > 1) {
+      DevBuf<double> tmp(1);
+      PICARD_CUDA(cudaMemcpyAsync(tmp.p, &t_total, sizeof(double), cudaMemcpyHostToDevice, st));
+      comm_allreduce_sum(comm, tmp.p, 1, st);
+      PICARD_CUDA(cudaMemcpyAsync(&t_total, tmp.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+      PICARD_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<double> mh, kh;
+    picard_stats_t stats;
+    memset(&stats, 0, sizeof stats);
+    const int nf = (int)n_features, nc = (int)n_components;
+    center_whiten_device(d_x, nf, n_samples, row_stride, nc, centering != 0, true, comm, guard.sm_count, st, mh, kh, t_total, &stats);
+    if (mean && centering) memcpy(mean, mh.data(), sizeof(double) * nf);
+    if (k) memcpy(k, kh.data(), sizeof(double) * nc * nf);
+  });
+}
+
 int picard_jade(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, int64_t max_iter, double tol, int32_t verbose,
                 int32_t device, double* w, int64_t* sweeps, char* err, size_t errlen) {
   return guarded(err, errlen, [&] {

@@ -45,6 +45,8 @@ struct PassGeom {
   static constexpr size_t SMEM_BYTES = 1024 + XS_BYTES + WS_BYTES + YS_BYTES + (size_t)NP * 8 + 64;
 };
 
+constexpr int PASS_MAX_BLOCKS_PER_SM = 8;  // grid <= sm_count * this: bounds the per-CTA partial workspace
+
 // packed partial layout of one CTA (padded to NP): [G NP^2 if WANT_G][H NP^2 if WANT_H][SD NP][SQ NP][LL NP]
 __host__ __device__ inline int pass_partial_size(int np, bool want_g, bool want_h) {
   return (want_g ? np * np : 0) + (want_h ? np * np : 0) + 3 * np;

@@ -15,7 +15,7 @@ static int launch_one(const PassLaunch& L, const CUtensorMap& tmap) {
     int b = 0;
     PICARD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, G::NTHREADS, G::SMEM_BYTES));
     if (b < 1) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: pass kernel does not fit on this device");
-    blocks_per_sm = b;
+    blocks_per_sm = b > PASS_MAX_BLOCKS_PER_SM ? PASS_MAX_BLOCKS_PER_SM : b;
   }
   const int64_t n_tiles = (L.t_local + G::BT - 1) / G::BT;
   int64_t grid = (int64_t)L.sm_count * blocks_per_sm;

@@ -15,7 +15,7 @@ int pass_padded_size(int n) {
 
 size_t pass_workspace_doubles(int n, int sm_count) {
   const int np = pass_padded_size(n);
-  return (size_t)sm_count * 8 * (size_t)pass_partial_size(np, true, true);
+  return (size_t)sm_count * PASS_MAX_BLOCKS_PER_SM * (size_t)pass_partial_size(np, true, true);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -539,9 +539,10 @@ __global__ void __launch_bounds__(BT1) jacobi_kernel(double* A, int n, double* V
 
 __global__ void symdecor_scale_kernel(const double* U, const double* evals, int n, double* scaled, int* status) {
   __shared__ double sh[33];
-  double mn = INFINITY;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) mn = fmin(mn, evals[i]);
-  mn = -block_max(-mn, sh);
+  // min eigenvalue (math.rs:21): block_max pads idle warps with 0, so reduce max(0, 1e-10 - ev) instead of -ev
+  double defect = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) defect = fmax(defect, (evals[i] < 1e-10 || evals[i] != evals[i]) ? 1.0 : 0.0);
+  const double mn = block_max(defect, sh) > 0.0 ? 0.0 : 1.0;
   if (threadIdx.x == 0) *status = (mn < 1e-10) ? PICARD_SINGULAR_MATRIX : PICARD_OK;
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) scaled[e] = U[e] * (1.0 / sqrt(evals[e % n]));
 }

@@ -1,0 +1,160 @@
+"""End-to-end GPU parity of the fit path (Picard::fit_with_config / transform, solver.rs:45-214) through the
+reference-facing API of picard_ica_b200 (ctypes over the C ABI), against the CPU oracle on identical X and
+w_init.  Bar (BASELINE.json north_star): Amari distance between the two unmixings <= 1e-6, iteration counts
+within +-1.  The shape-level assertions of the reference's own tests (solver.rs:288-408) are repeated too."""
+import numpy as np
+import pytest
+
+import _data
+import picard_ica_b200 as P
+from oracle import oracle as orc
+from picard_ica_b200 import ConfigBuilder, DensityType, Picard, PicardConfig, PicardError
+from picard_ica_b200.utils import amari_distance
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(res, ref, amari_tol=1e-6, iters_tol=1):
+    assert abs(res.n_iterations - ref.n_iterations) <= iters_tol, (res.n_iterations, ref.n_iterations)
+    assert res.converged == ref.converged
+    d = amari_distance(res.full_unmixing(), np.linalg.pinv(ref.full_unmixing()))
+    assert d <= amari_tol, d
+    return d
+
+
+def test_config1_reference_bench_case():
+    """BASELINE configs[0]: N=3 Laplace, T=10,000, tanh, whiten, ortho=false, data from the reference's own bench
+    generator (benches/benchmarks.rs:8-35)."""
+    x = _data.lcg_bench_data(3, 10_000, 42)
+    w0 = _data.orthogonal(3, 43)
+    res = Picard.fit_with_config(x, PicardConfig(ortho=False, w_init=w0))
+    ref = orc.fit(x, orc.Config(ortho=False, w_init=w0))
+    assert res.signs is None and ref.signs is None
+    _cmp(res, ref)
+    np.testing.assert_allclose(res.mean, ref.mean, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(res.whitening, ref.whitening, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(res.sources, ref.sources, rtol=0, atol=1e-6)
+    assert abs(res.gradient_norm - ref.gradient_norm) <= 1e-9
+
+
+@pytest.mark.parametrize("n,t,kind", [(8, 20_000, "mixed"), (16, 30_000, "laplace"), (64, 50_000, "mixed")])
+def test_picard_o_extended(n, t, kind):
+    """BASELINE configs[1]/[2] at sizes the oracle finishes in seconds: Picard-O, extended, tanh."""
+    x, a, _ = _data.mixture(n, t, seed=n, kind=kind)
+    w0 = _data.orthogonal(n, 43)
+    res = Picard.fit_with_config(x, PicardConfig(w_init=w0))
+    ref = orc.fit(x, orc.Config(w_init=w0))
+    assert res.converged
+    _cmp(res, ref)
+    np.testing.assert_array_equal(res.signs, ref.signs)
+    # and it actually separates the sources
+    assert amari_distance(res.full_unmixing(), a) < 0.05
+
+
+def test_nonortho_exp_density():
+    """BASELINE configs[3] shape in miniature: non-ortho, exp(alpha=0.1), Laplace sources."""
+    x, a, _ = _data.mixture(12, 40_000, seed=5, kind="laplace")
+    w0 = _data.orthogonal(12, 43)
+    cfg = dict(ortho=False, extended=False, w_init=w0)
+    res = Picard.fit_with_config(x, PicardConfig(density=DensityType.exp_with_alpha(0.1), **cfg))
+    ref = orc.fit(x, orc.Config(density=orc.EXP, alpha=0.1, **cfg))
+    _cmp(res, ref)
+
+
+def test_cube_density_subgaussian():
+    x, a, _ = _data.mixture(5, 20_000, seed=8, kind="uniform")
+    w0 = _data.orthogonal(5, 43)
+    res = Picard.fit_with_config(x, PicardConfig(density=DensityType.cube(), ortho=True, extended=False, w_init=w0, max_iter=200))
+    ref = orc.fit(x, orc.Config(density=orc.CUBE, ortho=True, extended=False, w_init=w0, max_iter=200))
+    _cmp(res, ref)
+
+
+def test_speculation_does_not_change_the_iterates():
+    """The speculative fused try is an execution strategy only: same iterate sequence with it disabled."""
+    x, _, _ = _data.mixture(10, 20_000, seed=2)
+    w0 = _data.orthogonal(10, 43)
+    a = Picard.fit_with_config(x, PicardConfig(w_init=w0))
+    b = Picard.fit_with_config(x, PicardConfig(w_init=w0, flags=P.FLAG_NO_SPECULATION))
+    assert a.n_iterations == b.n_iterations
+    np.testing.assert_allclose(a.unmixing, b.unmixing, rtol=0, atol=1e-12)
+    assert a.stats["fused_passes"] > 0 and b.stats["fused_passes"] == 0
+
+
+# ---- the reference's own solver tests (solver.rs:288-408), same assertions ---------------------------
+def _laplace_mix(n, t, seed):
+    return _data.mixture(n, t, seed, "laplace")[0]
+
+
+def test_fit_default():  # solver.rs:289-301
+    x = _laplace_mix(3, 1000, 42)
+    r = Picard.fit(x)
+    assert r.unmixing.shape == (3, 3) and r.sources.shape == (3, 1000)
+    assert r.whitening is not None and r.mean is not None
+
+
+def test_fit_with_config():  # solver.rs:304-318
+    x = _laplace_mix(4, 2000, 42)
+    cfg = ConfigBuilder().n_components(3).max_iter(100).tol(1e-6).random_state(42).build()
+    r = Picard.fit_with_config(x, cfg)
+    assert r.unmixing.shape == (3, 3) and r.sources.shape == (3, 2000) and r.whitening.shape == (3, 4)
+    assert r.n_iterations <= 100
+
+
+def test_transform_matches_sources():  # solver.rs:359-375
+    x = _laplace_mix(3, 1000, 7)
+    r = Picard.fit_with_config(x, PicardConfig(random_state=1))
+    y = Picard.transform(x, r)
+    assert y.shape == (3, 1000)
+    np.testing.assert_allclose(y, r.sources, rtol=0, atol=1e-9)
+    x2 = _laplace_mix(3, 333, 8)
+    np.testing.assert_allclose(Picard.transform(x2, r), r.full_unmixing() @ (x2 - r.mean[:, None]), rtol=0, atol=1e-10)
+
+
+def test_no_whiten():  # solver.rs:378-394 ; quirk Q13: n_components ignored
+    x = _laplace_mix(3, 1000, 9)
+    r = Picard.fit_with_config(x, PicardConfig(whiten=False, n_components=2, random_state=3, max_iter=50))
+    assert r.whitening is None and r.unmixing.shape == (3, 3)
+
+
+def test_no_centering():
+    x = _laplace_mix(3, 1000, 9) + 5.0
+    r = Picard.fit_with_config(x, PicardConfig(centering=False, random_state=3, max_iter=20))
+    assert r.mean is None
+
+
+def test_same_seed_same_result():
+    x = _laplace_mix(4, 3000, 10)
+    a = Picard.fit_with_config(x, PicardConfig(random_state=5))
+    b = Picard.fit_with_config(x, PicardConfig(random_state=5))
+    np.testing.assert_array_equal(a.unmixing, b.unmixing)
+
+
+def test_errors():
+    x = _laplace_mix(3, 100, 1)
+    with pytest.raises(PicardError.InvalidConfig) as e:  # solver.rs:397-407
+        Picard.fit_with_config(x, PicardConfig(fastica_it=5, jade_it=5))
+    assert e.value.parameter == "jade_it"
+    with pytest.raises(PicardError.InvalidDimensions):   # solver.rs:50-54
+        Picard.fit(np.zeros((0, 0)))
+    with pytest.raises(PicardError.InvalidDimensions):   # solver.rs:100-108
+        Picard.fit_with_config(x, PicardConfig(w_init=np.eye(2)))
+    with pytest.raises(PicardError.SingularMatrix):      # whitening.rs:72-79 (rank-deficient data)
+        Picard.fit(np.vstack([x[0], x[0], x[1]]))
+    with pytest.raises(PicardError.InvalidDimensions):   # whitening.rs:51-58 cannot trigger via fit (min()), transform mismatch
+        Picard.transform(np.zeros((5, 10)), Picard.fit(x))
+
+
+def test_not_converged_is_ok_not_error():
+    x = _laplace_mix(6, 5000, 3)
+    r = Picard.fit_with_config(x, PicardConfig(max_iter=2, random_state=0))
+    assert not r.converged and r.n_iterations == 2 and r.gradient_norm > 1e-7
+
+
+def test_odd_t_and_strided_input():
+    big = np.random.default_rng(0).standard_normal((5, 4000))
+    x = (_data.orthogonal(5, 1) @ np.sign(big) * np.abs(big) ** 1.5)[:, :3333]  # a view with row stride 4000
+    assert x.strides[0] == 4000 * 8
+    w0 = _data.orthogonal(5, 43)
+    res = Picard.fit_with_config(x, PicardConfig(w_init=w0))
+    ref = orc.fit(np.ascontiguousarray(x), orc.Config(w_init=w0))
+    _cmp(res, ref)

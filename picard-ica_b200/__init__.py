@@ -257,11 +257,8 @@ class PicardResult:
 
     def mixing(self) -> np.ndarray:  # result.rs:49-64 (host-side N x N, as in the reference)
         w = self.full_unmixing()
-        wtw = w.T @ w
-        try:
-            return np.linalg.solve(wtw, w.T)
-        except np.linalg.LinAlgError:
-            return w.T.copy()
+        inv = _invert_matrix(w.T @ w)
+        return inv @ w.T if inv is not None else w.T.copy()  # fallback: transpose (result.rs:62-63)
 
     def _to_c(self):
         r = _ffi.Result()
@@ -280,6 +277,23 @@ class PicardResult:
         r.unmixing = put(self.unmixing)
         r.mean = put(self.mean)
         return r, keep
+
+
+def _invert_matrix(m: np.ndarray):
+    """result.rs:67-129: Gauss-Jordan with partial pivoting; None when a pivot is below 1e-15."""
+    n = m.shape[0]
+    aug = np.hstack([np.array(m, dtype=np.float64), np.eye(n)])
+    for i in range(n):
+        max_row = i + int(np.argmax(np.abs(aug[i:, i])))
+        if max_row != i:
+            aug[[i, max_row]] = aug[[max_row, i]]
+        if abs(aug[i, i]) < 1e-15:
+            return None
+        aug[i] /= aug[i, i]
+        for k in range(n):
+            if k != i:
+                aug[k] -= aug[k, i] * aug[i]
+    return aug[:, n:].copy()
 
 
 def _from_c_result(r: _ffi.Result) -> PicardResult:

@@ -151,6 +151,12 @@ void picard_core_destroy(picard_core_t* c);
 int picard_eval_moments(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
                         int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device, double* gr,
                         double* sd, double* hr, double* sq, double* lrow, char* err, size_t errlen);
+/* Same on a DEVICE-resident matrix, `repeats` launches timed with CUDA events on the library's stream
+ * (avg_ms = mean duration of one pass incl. the partial reduction).  Bench / profiling hook. */
+int picard_eval_moments_device(const double* d_x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
+                               int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device,
+                               int32_t repeats, double* avg_ms, double* gr, double* sd, double* hr, double* sq, double* lrow,
+                               char* err, size_t errlen);
 /* The processed quantities of one iteration front (core.rs:215-293) plus the loss (core.rs:39-85) at
  * Y = W X: projected gradient g, Hessian approximation h, h_off, signs, sign_change, gradient norm, loss.
  * c = C matrix of the extended sign rule (NULL = identity); old_signs NULL = first iteration;

@@ -196,6 +196,35 @@ int picard_eval_moments(const double* x, int64_t n, int64_t n_samples, int64_t r
   });
 }
 
+int picard_eval_moments_device(const double* d_x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
+                               int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device, int32_t repeats,
+                               double* avg_ms, double* gr, double* sd, double* hr, double* sq, double* lrow, char* err, size_t errlen) {
+  return guarded(err, errlen, [&] {
+    if (mode < 0 || mode > 2) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'mode': must be 0, 1 or 2");
+    if (n <= 0 || n_samples <= 0 || !d_x) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
+    DeviceGuard guard(device);
+    picard_config_t c = hook_config(density_kind, alpha, want_h ? 0 : 1, 0, 0.01, guard.device);
+    config_validate(c);
+    cudaStream_t st;
+    PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
+    CoreSolver solver(d_x, (int)n, n_samples, row_stride, c, false, guard.sm_count, st);
+    solver.hook_moments(w, mode, want_h != 0, gr, sd, hr, sq, lrow);  // warm-up + results
+    if (repeats > 0) {
+      cudaEvent_t e0, e1;
+      PICARD_CUDA(cudaEventCreate(&e0)); PICARD_CUDA(cudaEventCreate(&e1));
+      PICARD_CUDA(cudaEventRecord(e0, st));
+      for (int r = 0; r < repeats; ++r) solver.hook_moments(nullptr, mode, want_h != 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+      PICARD_CUDA(cudaEventRecord(e1, st));
+      PICARD_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      PICARD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      if (avg_ms) *avg_ms = ms / repeats;
+    }
+  });
+}
+
 int picard_eval_point(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w, int32_t density_kind,
                       double alpha, int32_t ortho, int32_t extended, double lambda_min, const double* cmat, const double* old_signs,
                       const double* loss_signs, int32_t device, double* g, double* h, double* hoff, double* signs,

@@ -124,8 +124,10 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
   constexpr int MB = G::MB, NB = G::NB, WP = G::WPITCH, YP = G::YPITCH;
   static_assert(!(WANT_H && !WANT_G), "H needs the gradient moments");
 
-  extern __shared__ unsigned char smem_raw[];
-  double* xs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (SWIZZLE_128B atom) comes from the declaration: keeping the pointer arithmetic free of integer
+  // casts keeps every access in the shared address space (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double* xs = reinterpret_cast<double*>(smem_raw);
   double* ws = xs + G::STAGES * NP * G::BT;
   double* ys = ws + NP * WP;
   double* bs = ys + 2 * NP * YP;

@@ -71,6 +71,7 @@ typedef struct {
 
 #define PICARD_FLAG_NO_SPECULATION 1u /* line-search tries never carry the gradient moments (debug / ablation) */
 #define PICARD_FLAG_KEEP_SOURCES_ON_DEVICE 2u /* picard_fit_device: do not copy `sources` to the host */
+#define PICARD_FLAG_NO_Y_STORE 4u /* loss-only tries do not keep Y' (saves one N x T buffer; the gradient recomputes W X) */
 
 /* Measurement record filled by every fit / core run (not in the reference). */
 typedef struct {
@@ -82,6 +83,8 @@ typedef struct {
   int64_t ls_tries, fallbacks, sign_changes;
   int64_t kernel_launches; /* launches of this library's own kernels */
   double pass_ms_fused, pass_ms_grad, pass_ms_loss; /* summed device time of the pass kernels by kind */
+  int64_t grady_passes;    /* gradient passes served from the stored Y of an accepted loss-only try (2 N^2 T flop) */
+  double pass_ms_grady;
 } picard_stats_t;
 
 /* PicardResult (result.rs:7-33).  Buffers are malloc'd by the library and released by
@@ -146,7 +149,9 @@ void picard_core_destroy(picard_core_t* c);
 /* Raw moments of the pass kernels at Y = W X for host inputs (w NULL = identity):
  *   gr[i,j] = sum_t psi(y_it) y_jt ; sd[i] = sum_t psi'(y_it) ; hr[i,j] = sum_t psi'(y_it) y_jt^2 ;
  *   sq[i] = sum_t y_it^2 ; lrow[i] = sum_t loglik(y_it).        (core.rs:215-221,226,264,274 ; density.rs)
- * mode: 0 = fused (all), 1 = grad-only (lrow untouched), 2 = loss-only (gr, sd, hr untouched).
+ * mode: 0 = fused (all), 1 = grad-only (lrow untouched), 2 = loss-only (gr, sd, hr untouched),
+ *       3 = loss-only pass that stores Y, then the gradient moments from the stored Y (the two-kernel path an
+ *           accepted loss-only line-search try takes).
  * Any output pointer may be NULL.  hr is only computed when want_h != 0. */
 int picard_eval_moments(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
                         int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device, double* gr,

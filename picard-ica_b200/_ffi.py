@@ -39,6 +39,7 @@ class Stats(C.Structure):  # picard_stats_t
         ("fused_passes", C.c_int64), ("grad_passes", C.c_int64), ("loss_passes", C.c_int64),
         ("ls_tries", C.c_int64), ("fallbacks", C.c_int64), ("sign_changes", C.c_int64), ("kernel_launches", C.c_int64),
         ("pass_ms_fused", C.c_double), ("pass_ms_grad", C.c_double), ("pass_ms_loss", C.c_double),
+        ("grady_passes", C.c_int64), ("pass_ms_grady", C.c_double),
     ]
 
     def as_dict(self):
@@ -56,6 +57,7 @@ class Result(C.Structure):  # picard_result_t
 
 FLAG_NO_SPECULATION = 1
 FLAG_KEEP_SOURCES_ON_DEVICE = 2
+FLAG_NO_Y_STORE = 4
 UNIQUE_ID_BYTES = 128
 
 _lib = None

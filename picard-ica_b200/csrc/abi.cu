@@ -182,7 +182,7 @@ int picard_eval_moments(const double* x, int64_t n, int64_t n_samples, int64_t r
                         double alpha, int32_t mode, int32_t want_h, int32_t device, double* gr, double* sd, double* hr, double* sq,
                         double* lrow, char* err, size_t errlen) {
   return guarded(err, errlen, [&] {
-    if (mode < 0 || mode > 2) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'mode': must be 0, 1 or 2");
+    if (mode < 0 || mode > 3) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'mode': must be 0, 1, 2 or 3");
     DeviceGuard guard(device);
     Staged xs(x, n, n_samples, row_stride, 0);
     PICARD_CUDA(cudaStreamSynchronize(0));
@@ -200,7 +200,7 @@ int picard_eval_moments_device(const double* d_x, int64_t n, int64_t n_samples, 
                                int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device, int32_t repeats,
                                double* avg_ms, double* gr, double* sd, double* hr, double* sq, double* lrow, char* err, size_t errlen) {
   return guarded(err, errlen, [&] {
-    if (mode < 0 || mode > 2) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'mode': must be 0, 1 or 2");
+    if (mode < 0 || mode > 4) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'mode': must be 0..4");
     if (n <= 0 || n_samples <= 0 || !d_x) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
     DeviceGuard guard(device);
     picard_config_t c = hook_config(density_kind, alpha, want_h ? 0 : 1, 0, 0.01, guard.device);
@@ -209,7 +209,8 @@ int picard_eval_moments_device(const double* d_x, int64_t n, int64_t n_samples, 
     PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
     CoreSolver solver(d_x, (int)n, n_samples, row_stride, c, false, guard.sm_count, st);
-    solver.hook_moments(w, mode, want_h != 0, gr, sd, hr, sq, lrow);  // warm-up + results
+    // mode 4 = the stored-Y gradient kernel alone: fill the store first (mode 3 = loss pass with store + grady)
+    solver.hook_moments(w, mode == 4 ? 3 : mode, want_h != 0, gr, sd, hr, sq, lrow);  // warm-up + results
     if (repeats > 0) {
       cudaEvent_t e0, e1;
       PICARD_CUDA(cudaEventCreate(&e0)); PICARD_CUDA(cudaEventCreate(&e1));

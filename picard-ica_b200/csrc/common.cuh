@@ -33,6 +33,6 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 enum : int { DENS_TANH = 0, DENS_EXP = 1, DENS_CUBE = 2, DENS_LINEAR = 3 };
 
 // Pass modes
-enum : int { PASS_FUSED = 0, PASS_GRAD = 1, PASS_LOSS = 2, PASS_APPLY = 3 };
+enum : int { PASS_FUSED = 0, PASS_GRAD = 1, PASS_LOSS = 2, PASS_APPLY = 3, PASS_GRADY = 4 /* gradient moments from a stored Y */ };
 
 }  // namespace picard

@@ -66,6 +66,11 @@ CoreSolver::CoreSolver(const double* d_x, int n, int64_t t_local, int64_t ldx, c
   mem_r_ = b + omr; mom_cur_ = b + omc; mom_trial_ = b + omt; lu_work_ = b + olu;
   ew_.As = b + oAs; ew_.term0 = b + ot0; ew_.term1 = b + ot1; ew_.res0 = b + or0; ew_.res1 = b + or1; ew_.slots = b + osl;
   partial_.alloc(pass_workspace_doubles(n, sm_count_));
+  if (!(cfg.flags & PICARD_FLAG_NO_Y_STORE)) {
+    // one extra N x T buffer: an accepted loss-only try leaves its Y' here, so the next gradient pass skips W X.
+    // Not having the memory is not an error: the gradient pass then recomputes from X.
+    try { ybuf_.alloc((size_t)n * (size_t)ldx_); } catch (const Error&) { cudaGetLastError(); ybuf_.release(); }
+  }
   PICARD_CUDA(cudaEventCreate(&ev_a_));
   PICARD_CUDA(cudaEventCreate(&ev_b_));
   PICARD_CUDA(cudaEventCreate(&ev_run0_));
@@ -88,15 +93,18 @@ void CoreSolver::reset() {
   PICARD_CUDA(cudaMemcpyAsync(signs_, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st_));      // core.rs:182
   PICARD_CUDA(cudaMemcpyAsync(old_signs_, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st_));  // core.rs:183
   PICARD_CUDA(cudaStreamSynchronize(st_));
-  iter_ = 0; n_iterations_ = 0; converged_ = false; started_ = false; have_cur_ = false; speculate_next_ = true;
+  iter_ = 0; n_iterations_ = 0; converged_ = false; started_ = false; have_cur_ = false; speculate_next_ = true; ybuf_valid_ = false;
   gradient_norm_ = 1.0; current_loss_ = 0.0;
 }
 
-void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, double alpha, double* d_mom) {
+void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, double alpha, double* d_mom, bool store_y) {
   PassLaunch L;
-  L.d_x = d_x_; L.ldx = ldx_; L.t_local = t_local_; L.n_in = dims_.n; L.n_out = dims_.n;
+  L.d_x = (mode == PASS_GRADY) ? ybuf_.p : d_x_; L.ldx = ldx_; L.t_local = t_local_; L.n_in = dims_.n; L.n_out = dims_.n;
   L.d_w = d_w; L.ldw = dims_.n; L.d_bias = nullptr; L.dens = dens; L.alpha = alpha; L.mode = mode; L.want_h = want_h;
-  L.d_partial = partial_.p; L.d_mom = d_mom; L.d_out = nullptr; L.ld_out = 0; L.sm_count = sm_count_; L.stream = st_;
+  L.d_partial = partial_.p; L.d_mom = d_mom; L.sm_count = sm_count_; L.stream = st_;
+  const bool store = store_y && mode == PASS_LOSS && ybuf_.p != nullptr;
+  L.d_out = store ? ybuf_.p : nullptr; L.ld_out = store ? ldx_ : 0;
+  if (mode == PASS_LOSS) ybuf_valid_ = store;
   PICARD_CUDA(cudaEventRecord(ev_a_, st_));
   stats_.kernel_launches += launch_pass(L);
   PICARD_CUDA(cudaEventRecord(ev_b_, st_));
@@ -106,6 +114,7 @@ void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
     const size_t nn = (size_t)n * n;
     if (mode == PASS_LOSS) comm_allreduce_sum(comm_, d_mom + mom_off_sq(n), 2 * (size_t)n, st_);
     else if (mode == PASS_FUSED) comm_allreduce_sum(comm_, d_mom, nn + 3 * (size_t)n + (want_h ? nn : 0), st_);
+    // PASS_GRAD and PASS_GRADY produce [Gr, Sd, Sq] (+ Hr)
     else comm_allreduce_sum2(comm_, d_mom, nn + 2 * (size_t)n, want_h ? d_mom + mom_off_hr(n) : nullptr, want_h ? nn : 0, st_);
   }
   last_pass_mode_ = mode;
@@ -114,8 +123,9 @@ void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
 void CoreSolver::pass(const double* d_w, int mode, double* d_mom) {
   if (mode == PASS_FUSED) stats_.fused_passes++;
   else if (mode == PASS_GRAD) stats_.grad_passes++;
+  else if (mode == PASS_GRADY) stats_.grady_passes++;
   else stats_.loss_passes++;
-  eval_pass(d_w, mode, need_h_ && mode != PASS_LOSS, dens_, alpha_, d_mom);
+  eval_pass(d_w, mode, need_h_, dens_, alpha_, d_mom, /*store_y=*/true);  // LOSS mode: want_h = the Sq row sums only
 }
 
 void CoreSolver::fetch_scalars() {
@@ -127,6 +137,7 @@ void CoreSolver::fetch_scalars() {
     if (last_pass_mode_ == PASS_FUSED) stats_.pass_ms_fused += ms;
     else if (last_pass_mode_ == PASS_GRAD) stats_.pass_ms_grad += ms;
     else if (last_pass_mode_ == PASS_LOSS) stats_.pass_ms_loss += ms;
+    else if (last_pass_mode_ == PASS_GRADY) stats_.pass_ms_grady += ms;
   }
   last_pass_mode_ = -1;
 }
@@ -172,7 +183,7 @@ int64_t CoreSolver::run(int64_t max_new) {
   int64_t done = 0;
   while (done < max_new && iter_ < cfg_.max_iter && !converged_) {
     if (!have_cur_) {  // gradient moments of the current iterate are missing (a loss-only try was accepted)
-      pass(W_, PASS_GRAD, mom_cur_);
+      pass(W_, ybuf_valid_ ? PASS_GRADY : PASS_GRAD, mom_cur_);  // its Y' is still in ybuf_: no W X product needed
       have_cur_ = true;
     }
     small::FrontArgs fa;
@@ -247,7 +258,14 @@ void CoreSolver::hook_moments(const double* w_host, int mode, bool want_h, doubl
   const int n = dims_.n;
   const size_t nn = (size_t)n * n;
   if (w_host) PICARD_CUDA(cudaMemcpyAsync(W_, w_host, sizeof(double) * nn, cudaMemcpyHostToDevice, st_));
-  eval_pass(W_, mode, want_h, dens_, alpha_, mom_cur_);
+  if (mode == 3) {  // the two-kernel path of an accepted loss-only try: LOSS pass storing Y', then moments from the stored Y'
+    if (!ybuf_.p) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: no memory for the Y store");
+    eval_pass(W_, PASS_LOSS, want_h, dens_, alpha_, mom_cur_, true);
+    eval_pass(W_, PASS_GRADY, want_h, dens_, alpha_, mom_cur_);
+    mode = PASS_FUSED;  // all sections are valid now
+  } else {
+    eval_pass(W_, mode, want_h, dens_, alpha_, mom_cur_);
+  }
   auto get = [&](double* dst, int64_t off, size_t cnt) {
     if (dst) PICARD_CUDA(cudaMemcpyAsync(dst, mom_cur_ + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st_));
   };

@@ -1,18 +1,24 @@
 // Elementwise densities of the fused pass: psi, psi', log-likelihood (density.rs:50-63, 91-103, 122-130).
 //
-// On B200 DMMA and DFMA issue to the SAME FP64 pipe (profiles/microbench/fp64_pipes_r01.jsonl: mixed
-// kernels are additive), so every FP64 instruction spent here is taken from the contraction budget.
-// The transcendental kernels below therefore (a) share one e = exp(-2 alpha |y|) between tanh, 1 - tanh^2
-// and the log-likelihood, (b) use argument ranges known a priori (x <= 0; 1 + e in (1, 2]) to drop all
-// special-case handling, (c) take reciprocal seeds from the SFU (MUFU.RCP64H), which is a separate pipe.
-// Accuracy target: <= ~1e-14 relative per element (the parity bar on G, h, loss is 1e-10).
-// Everything is __host__ __device__ so the polynomials can be checked on the CPU (tests/test_density_host).
+// On B200 DMMA and DFMA issue to the SAME FP64 pipe (profiles/microbench/fp64_pipes_r01.jsonl: mixed kernels are
+// additive; ncu on the pass kernel: DMMA sub-pipe % + FP64 pipe % = SM throughput %), so every FP64 instruction
+// spent here is taken from the contraction budget (4 N flop per element = 8 pipe-instructions at N = 128).
+// Everything below is therefore built to minimise FP64-pipe instructions, moving work to pipes that are idle:
+//   * exp: Cody-Waite reduction to |r| <= ln2/512 with a 256-entry table of 2^(j/256) in shared memory (LSU) and
+//     the exponent inserted by integer adds (ALU): 9 FP64 instructions instead of 18 for a table-free degree-12 series;
+//   * log(1 + e), 1 + e in [1, 2]: 128-entry table {1/v0, -log(1/v0)} indexed by the top mantissa bits (ALU),
+//     u = fma(v, 1/v0, -1), |u| <= 2^-8, degree-5 series: 7 FP64 instructions instead of 22;
+//   * reciprocal seeds from the SFU (MUFU.RCP64H) + 2 Newton steps; |y| and sign transfers by integer ops;
+//   * range clamps by integer min on the high word; one e = exp(-2 alpha |y|) shared by tanh, 1 - tanh^2 and log-lik.
+// Accuracy: <= ~1e-15 relative per element (the parity bar on the sums G, h, loss is 1e-10; measured ~1e-13).
+// Everything is host-callable so the polynomials are checked on the CPU (tests/test_density_host.py).
 #pragma once
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 
 #include "common.cuh"
+#include "density_tables.inc"
 
 #if defined(__CUDACC__)
 #define PICARD_HD __host__ __device__ __forceinline__
@@ -23,6 +29,10 @@
 namespace picard {
 namespace dmath {
 
+constexpr int EXP_TAB_N = 256;  // doubles
+constexpr int LOG_TAB_N = 256;  // doubles: 128 pairs {1/v0, -log(1/v0)}
+constexpr int TAB_DOUBLES = EXP_TAB_N + LOG_TAB_N;
+
 PICARD_HD int lo32(double t) {
 #ifdef __CUDA_ARCH__
   return __double2loint(t);
@@ -30,12 +40,25 @@ PICARD_HD int lo32(double t) {
   uint64_t u; memcpy(&u, &t, 8); return (int)(uint32_t)u;
 #endif
 }
-PICARD_HD double add_exponent(double p, int k) {  // p * 2^k for normal results
+PICARD_HD int hi32(double t) {
 #ifdef __CUDA_ARCH__
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  return __double2hiint(t);
 #else
-  uint64_t u; memcpy(&u, &p, 8); u += (uint64_t)((int64_t)k << 52); double o; memcpy(&o, &u, 8); return o;
+  uint64_t u; memcpy(&u, &t, 8); return (int)(uint32_t)(u >> 32);
 #endif
+}
+PICARD_HD double make_double(int hi, int lo) {
+#ifdef __CUDA_ARCH__
+  return __hiloint2double(hi, lo);
+#else
+  uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double o; memcpy(&o, &u, 8); return o;
+#endif
+}
+PICARD_HD double add_exponent(double p, int k) { return make_double(hi32(p) + (k << 20), lo32(p)); }  // p * 2^k, normal results
+// non-negative doubles order like their high words: min(a, limit) on the ALU, not the FP64 pipe (limit given by its high word)
+PICARD_HD double clamp_hi(double a_nonneg, int hi_limit) {
+  const int h = hi32(a_nonneg);
+  return make_double(h < hi_limit ? h : hi_limit, lo32(a_nonneg));
 }
 // ~20-bit reciprocal seed.  Device: MUFU.RCP64H (SFU pipe, not the FP64 pipe).
 PICARD_HD double rcp_seed(double d) {
@@ -47,7 +70,7 @@ PICARD_HD double rcp_seed(double d) {
   return (double)(1.0f / (float)d);
 #endif
 }
-// 1/d for d in a benign range (no zero/inf/denormal handling): seed + 2 Newton steps (quadratic: 2^-20 -> 2^-80).
+// 1/d for d in a benign range (no zero/inf/denormal handling): seed + 2 Newton steps (2^-20 -> 2^-80).
 PICARD_HD double rcp_nr(double d) {
   double r = rcp_seed(d);
   double e = fma(-d, r, 1.0);
@@ -57,95 +80,112 @@ PICARD_HD double rcp_nr(double d) {
   return r;
 }
 
-// exp(x) for x <= ~0 (any x in [-700, 700] works); x below -700 returns exp(-700) ~ 1e-304 (never matters:
-// it is only ever added to 1).  Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-12 Taylor
-// (truncation <= 1.7e-16 relative at the interval ends), exponent inserted by integer add.
-PICARD_HD double exp_nonpos(double x) {
-  x = fmax(x, -700.0);
-  const double L2E = 1.4426950408889634074, LN2HI = 6.93147180369123816490e-01, LN2LO = 1.90821492927058770002e-10;
-  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rint() by add/sub, integer lands in the low word
-  double t = fma(x, L2E, MAGIC);
-  double kd = t - MAGIC;
-  int k = lo32(t);
-  double r = fma(kd, -LN2HI, x);
-  r = fma(kd, -LN2LO, r);
-  double p = 2.08767569878680989792e-09;            // 1/12!
-  p = fma(p, r, 2.50521083854417187751e-08);        // 1/11!
-  p = fma(p, r, 2.75573192239858906526e-07);        // 1/10!
-  p = fma(p, r, 2.75573192239858906526e-06);        // 1/9!
-  p = fma(p, r, 2.48015873015873015873e-05);        // 1/8!
-  p = fma(p, r, 1.98412698412698412698e-04);        // 1/7!
-  p = fma(p, r, 1.38888888888888888889e-03);        // 1/6!
-  p = fma(p, r, 8.33333333333333333333e-03);        // 1/5!
-  p = fma(p, r, 4.16666666666666666667e-02);        // 1/4!
-  p = fma(p, r, 1.66666666666666666667e-01);        // 1/3!
+// exp(x) for x in [-700, 700] (callers clamp): x = n ln2/256 + r, |r| <= ln2/512; exp(r) - 1 by a degree-4 series
+// (truncation r^5/120 <= 4e-17); e = T[n & 255] (1 + q) 2^(n >> 8).  T = 2^(j/256) in shared memory.
+PICARD_HD double exp_tab(double x, const double* __restrict__ T) {
+  const double C = 369.32993046757462709;  // 256 / ln 2
+  const double LHI = 6.93147180369123816490e-01 / 256.0, LLO = 1.90821492927058770002e-10 / 256.0;  // ln2/256 split; LHI has 32 trailing zero bits
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rint() by add/sub, the integer lands in the low word
+  const double t = fma(x, C, MAGIC);
+  const double kd = t - MAGIC;
+  const int n = lo32(t);
+  double r = fma(kd, -LHI, x);
+  r = fma(kd, -LLO, r);
+  double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return add_exponent(p, k);
+  const double q = p * r;
+  const double tj = T[n & (EXP_TAB_N - 1)];
+  return add_exponent(fma(tj, q, tj), n >> 8);
 }
 
-// log(1 + e) for e in [0, 1]:  1+e in [1,2]; fold to [sqrt(1/2), sqrt 2] by an optional halving, then
-// log1p(f) = 2 atanh(s), s = f / (2 + f), |s| <= 0.1716, series to s^17 (truncation <= 9e-16 relative).
-PICARD_HD double log1p_unit(double e) {
-  const double SQRT2M1 = 0.41421356237309504880, LN2 = 0.69314718055994530942;
-  bool big = e > SQRT2M1;
-  double f = big ? fma(e, 0.5, -0.5) : e;
-  double d = 2.0 + f;
-  double s = f * rcp_nr(d);
-  double z = s * s;
-  double p = 2.0 / 17.0;
-  p = fma(p, z, 2.0 / 15.0);
-  p = fma(p, z, 2.0 / 13.0);
-  p = fma(p, z, 2.0 / 11.0);
-  p = fma(p, z, 2.0 / 9.0);
-  p = fma(p, z, 2.0 / 7.0);
-  p = fma(p, z, 2.0 / 5.0);
-  p = fma(p, z, 2.0 / 3.0);
-  double res = fma(s * z, p, s + s);
-  return big ? res + LN2 : res;
+// log(v) for v in [1, 2]: i = top 7 mantissa bits, v0 = 1 + (i + 1/2)/128, u = v/v0 - 1 (|u| <= 2^-8),
+// log v = -log(1/v0) + (u - u^2/2 + u^3/3 - u^4/4 + u^5/5)   (truncation u^6/6 <= 6e-16 absolute).
+PICARD_HD double log_1_2(double v, const double* __restrict__ LT) {
+  int i = (hi32(v) - 0x3FF00000) >> 13;
+  i = i < 127 ? i : 127;  // v == 2.0 exactly
+#ifdef __CUDA_ARCH__
+  const double2 rl = reinterpret_cast<const double2*>(LT)[i];
+  const double r0 = rl.x, l0 = rl.y;
+#else
+  const double r0 = LT[2 * i], l0 = LT[2 * i + 1];
+#endif
+  const double u = fma(v, r0, -1.0);
+  double p = fma(u, 0.2, -0.25);
+  p = fma(p, u, 1.0 / 3.0);
+  p = fma(p, u, -0.5);
+  p = p * u;
+  return fma(p, u, u) + l0;
 }
 
 }  // namespace dmath
 
-// One element of the density.  NEED_PSI: psi and psi' wanted; NEED_LL: log-likelihood wanted.
+// Constants of one density, prepared on the host.
+struct DensParams {
+  double alpha, inv_alpha;
+  double xscale;   // tanh: -2 alpha (x = xscale * |y|) ; exp: -alpha / 2 (x = xscale * y^2)
+  int hi_limit;    // high word of the clamp on |y| (tanh) or y^2 (exp) that keeps x >= -700
+};
+inline DensParams make_dens_params(int dens, double alpha) {
+  DensParams d;
+  d.alpha = alpha; d.inv_alpha = 1.0 / alpha;
+  d.xscale = dens == DENS_TANH ? -2.0 * alpha : -0.5 * alpha;
+  const double lim = 700.0 / std::fabs(d.xscale);
+  d.hi_limit = dmath::hi32(lim);
+  return d;
+}
+
+// One element of the density; accumulates the row sums itself so each mode pays only for what it needs.
 //   tanh (density.rs:50-63):  psi = tanh(a y), psi' = a (1 - psi^2), loglik = |y| + ln(1 + exp(-2 a |y|)) / a
 //   exp  (density.rs:91-103): k = exp(-a y^2 / 2), psi = y k, psi' = (1 - a y^2) k, loglik = -k / a
 //   cube (density.rs:122-130): psi = y^3, psi' = 3 y^2, loglik = y^4 / 4
 //   linear (internal): psi = y, psi' = 1, loglik = y^2 / 2   (covariance SYRK of the whitening step)
+// NEED_PSI: psi / psi' wanted (psi' is added to sd);  NEED_LL: log-likelihood wanted (added to sl).
+// tab: [exp table 256][log table 256] (shared memory on the device).
 template <int DENS, bool NEED_PSI, bool NEED_LL>
-PICARD_HD void density_eval(double y, double alpha, double inv_alpha, double& psi, double& psid, double& ll) {
+PICARD_HD void density_eval(double y, const DensParams& dp, const double* __restrict__ tab, double& psi, double& psid, double& sd,
+                            double& sl) {
   if (DENS == DENS_TANH) {
-    double ay = fabs(y);
-    double e = dmath::exp_nonpos(-2.0 * alpha * ay);
+    const double ay = fabs(y);
+    const double x = dmath::clamp_hi(ay, dp.hi_limit) * dp.xscale;
+    const double e = dmath::exp_tab(x, tab);
+    const double v = 1.0 + e;
     if (NEED_PSI) {
-      double r = dmath::rcp_nr(1.0 + e);
-      double th = (1.0 - e) * r;                  // tanh(alpha |y|)
-      psi = copysign(th, y * alpha);              // tanh(alpha y)
-      psid = alpha * fma(-th, th, 1.0);
+      const double r = dmath::rcp_nr(v);
+      const double th = (1.0 - e) * r;            // tanh(alpha |y|)
+      psi = copysign(th, y * dp.alpha);           // tanh(alpha y): sign transfer on the ALU (alpha > 0 in practice)
+      psid = dp.alpha * fma(-th, th, 1.0);
+      sd += psid;
     }
-    if (NEED_LL) ll = fma(dmath::log1p_unit(e), inv_alpha, ay);
+    if (NEED_LL) {
+      sl += ay;
+      sl = fma(dmath::log_1_2(v, tab + dmath::EXP_TAB_N), dp.inv_alpha, sl);
+    }
   } else if (DENS == DENS_EXP) {
-    double y2 = y * y;
-    double k = dmath::exp_nonpos(-0.5 * alpha * y2);
+    const double y2 = y * y;
+    const double x = dmath::clamp_hi(y2, dp.hi_limit) * dp.xscale;
+    const double k = dmath::exp_tab(x, tab);
     if (NEED_PSI) {
       psi = y * k;
-      psid = fma(-alpha, y2, 1.0) * k;
+      psid = fma(-dp.alpha, y2, 1.0) * k;
+      sd += psid;
     }
-    if (NEED_LL) ll = -k * inv_alpha;
+    if (NEED_LL) sl = fma(-k, dp.inv_alpha, sl);
   } else if (DENS == DENS_CUBE) {
-    double y2 = y * y;
+    const double y2 = y * y;
     if (NEED_PSI) {
       psi = y2 * y;
       psid = 3.0 * y2;
+      sd += psid;
     }
-    if (NEED_LL) ll = 0.25 * (y2 * y2);
+    if (NEED_LL) sl = fma(0.25 * y2, y2, sl);
   } else {
     if (NEED_PSI) {
       psi = y;
       psid = 1.0;
+      sd += 1.0;
     }
-    if (NEED_LL) ll = 0.5 * y * y;
+    if (NEED_LL) sl = fma(0.5 * y, y, sl);
   }
 }
 

@@ -87,7 +87,7 @@ class CoreSolver {
   int n() const { return dims_.n; }
 
   // one evaluation of the pass at an arbitrary W into a moment buffer (test hook + internal use)
-  void eval_pass(const double* d_w, int mode, bool want_h, int dens, double alpha, double* d_mom);
+  void eval_pass(const double* d_w, int mode, bool want_h, int dens, double alpha, double* d_mom, bool store_y = false);
   // test hooks (picard_eval_moments / picard_eval_point): host in, host out
   void hook_moments(const double* w_host, int mode, bool want_h, double* gr, double* sd, double* hr, double* sq, double* lrow);
   void hook_point(const double* w_host, const double* c_host, const double* old_signs_host, const double* loss_signs_host,
@@ -112,6 +112,8 @@ class CoreSolver {
 
   DevBuf<double> store_;   // all N x N state in one allocation
   DevBuf<double> partial_;
+  DevBuf<double> ybuf_;    // Y' of the last loss-only try (n x ldx_), empty when PICARD_FLAG_NO_Y_STORE or out of memory
+  bool ybuf_valid_ = false;
   DevBuf<CoreScalars> sc_dev_;
   PinnedBuf<CoreScalars> sc_host_;
   // views into store_

@@ -29,6 +29,9 @@ void config_validate(const picard_config_t& c) {  // config.rs:104-142, same ord
   if (c.m <= 0) fail("m", "L-BFGS memory size must be at least 1");
   if (c.fastica_it >= 0 && c.jade_it >= 0) fail("jade_it", "cannot use both fastica_it and jade_it; choose one warm start method");
   if (c.density_kind < 0 || c.density_kind > 2) fail("density", "unknown density kind");
+  // not checked by the reference (density.rs:31-34,72-75 accept any alpha); alpha <= 0 makes exp(-2 alpha |y|) overflow there
+  // and is rejected loudly here because the device kernels rely on exp arguments <= 0
+  if (c.density_kind != PICARD_DENSITY_CUBE && !(c.alpha > 0.0)) fail("density", "alpha must be positive");
 }
 
 // splitmix64 stream; u = ((next >> 11) + 0.5) 2^-53; Box-Muller, both outputs used in order.  This is the
@@ -250,6 +253,7 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   stats.ls_tries = cs.ls_tries; stats.fallbacks = cs.fallbacks; stats.sign_changes = cs.sign_changes;
   stats.kernel_launches += cs.kernel_launches;
   stats.pass_ms_fused = cs.pass_ms_fused; stats.pass_ms_grad = cs.pass_ms_grad; stats.pass_ms_loss = cs.pass_ms_loss;
+  stats.grady_passes = cs.grady_passes; stats.pass_ms_grady = cs.pass_ms_grady;
   const bool keep_dev = (cfg.flags & PICARD_FLAG_KEEP_SOURCES_ON_DEVICE) != 0;
   double* host_sources = nullptr;
   if (d_sources) {

@@ -42,7 +42,8 @@ struct PassGeom {
   static constexpr size_t XS_BYTES = (size_t)STAGES * NP * BT * 8;
   static constexpr size_t WS_BYTES = (size_t)NP * WPITCH * 8;
   static constexpr size_t YS_BYTES = (size_t)2 * NP * YPITCH * 8;
-  static constexpr size_t SMEM_BYTES = 1024 + XS_BYTES + WS_BYTES + YS_BYTES + (size_t)NP * 8 + 64;
+  static constexpr size_t TAB_BYTES = (size_t)dmath::TAB_DOUBLES * 8;  // exp / log lookup tables (density.cuh)
+  static constexpr size_t SMEM_BYTES = XS_BYTES + WS_BYTES + YS_BYTES + (size_t)NP * 8 + TAB_BYTES + 64;
 };
 
 constexpr int PASS_MAX_BLOCKS_PER_SM = 8;  // grid <= sm_count * this: bounds the per-CTA partial workspace
@@ -66,11 +67,15 @@ struct PassParams {
   int n_out, n_in, ldw;
   int64_t t_local;     // samples in this shard
   int64_t n_tiles;     // ceil(t_local / 16)
-  double alpha, inv_alpha;
+  DensParams dp;
   double* partial;     // [gridDim.x][pass_partial_size]
   double* out;         // APPLY: (n_out x t_local), leading dimension ld_out (even)
   int64_t ld_out;
 };
+
+// lookup tables of density.cuh in global memory (one copy per translation unit); staged into shared memory per CTA
+static __device__ const double g_exp_tab[dmath::EXP_TAB_N] = PICARD_EXP_TAB_INIT;
+static __device__ const double g_log_tab[dmath::LOG_TAB_N] = PICARD_LOG_TAB_INIT;
 
 namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,6 +111,22 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
+// Decoupled stage recycling: every warp calls this once per tile after its last read of the stage; the warp that
+// arrives last (shared-memory counter) runs `refill` (re-arms the mbarrier and issues the next TMA load).
+template <int NWARPS, typename F>
+__device__ __forceinline__ void stage_release(int* counter, int lane, F&& refill) {
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();                       // this warp's shared-memory reads of the stage are done
+    const int old = atomicAdd(counter, 1);
+    if (old == NWARPS - 1) {
+      atomicExch(counter, 0);
+      __threadfence_block();
+      fence_proxy_async();                       // generic-proxy reads before the async-proxy (TMA) overwrite
+      refill();
+    }
+  }
+}
 // FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -121,8 +142,11 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
   constexpr bool WANT_G = (MODE == PASS_FUSED || MODE == PASS_GRAD);
   constexpr bool WANT_L = (MODE == PASS_FUSED || MODE == PASS_LOSS);
   constexpr bool APPLY = (MODE == PASS_APPLY);
+  constexpr bool WANT_HM = WANT_G && WANT_H;  // the H matrix; in LOSS mode WANT_H only asks for the row sums of y^2
+  constexpr bool WANT_SQ = WANT_H;            // Sq is used by the non-ortho Hessian / loss only (core.rs:80-81, 274)
+  constexpr bool HAS_BIAS = APPLY || DENS == DENS_LINEAR;  // centering folded into the pass: never on the core-loop path
+  constexpr bool NEED_TAB = !APPLY && (DENS == DENS_TANH || DENS == DENS_EXP);
   constexpr int MB = G::MB, NB = G::NB, WP = G::WPITCH, YP = G::YPITCH;
-  static_assert(!(WANT_H && !WANT_G), "H needs the gradient moments");
 
   // 1024-byte alignment (SWIZZLE_128B atom) comes from the declaration: keeping the pointer arithmetic free of integer
   // casts keeps every access in the shared address space (LDS/STS instead of generic LD/ST)
@@ -131,7 +155,9 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
   double* ws = xs + G::STAGES * NP * G::BT;
   double* ys = ws + NP * WP;
   double* bs = ys + 2 * NP * YP;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(bs + NP);
+  double* tab = bs + NP;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tab + dmath::TAB_DOUBLES);
+  int* cnt = reinterpret_cast<int*>(bar + G::STAGES);  // per-stage release counters (LOSS mode: warps run decoupled)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int j = lane & 3, c = lane >> 2;
@@ -144,9 +170,11 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
     ws[i * WP + 8 * (kk >> 3) + 4 * (kk & 1) + ((kk & 7) >> 1)] = v;
   }
   for (int i = tid; i < NP; i += G::NTHREADS) bs[i] = (p.bias != nullptr && i < p.n_out) ? p.bias[i] : 0.0;
+  if (NEED_TAB)
+    for (int i = tid; i < dmath::EXP_TAB_N; i += G::NTHREADS) { tab[i] = g_exp_tab[i]; tab[dmath::EXP_TAB_N + i] = g_log_tab[i]; }
   if (tid == 0) {
     ptx::prefetch_tmap(&tmap);
-    for (int s = 0; s < G::STAGES; ++s) ptx::mbar_init(&bar[s], 1);
+    for (int s = 0; s < G::STAGES; ++s) { ptx::mbar_init(&bar[s], 1); cnt[s] = 0; }
     ptx::fence_barrier_init();
   }
   __syncthreads();
@@ -163,15 +191,15 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
 
   // ---- persistent accumulators
   double gacc[WANT_G ? MB : 1][WANT_G ? NB : 1][2];
-  double hacc[WANT_H ? MB : 1][WANT_H ? NB : 1][2];
+  double hacc[WANT_HM ? MB : 1][WANT_HM ? NB : 1][2];
 #pragma unroll
   for (int a = 0; a < (WANT_G ? MB : 1); ++a)
 #pragma unroll
     for (int b = 0; b < (WANT_G ? NB : 1); ++b) gacc[a][b][0] = gacc[a][b][1] = 0.0;
 #pragma unroll
-  for (int a = 0; a < (WANT_H ? MB : 1); ++a)
+  for (int a = 0; a < (WANT_HM ? MB : 1); ++a)
 #pragma unroll
-    for (int b = 0; b < (WANT_H ? NB : 1); ++b) hacc[a][b][0] = hacc[a][b][1] = 0.0;
+    for (int b = 0; b < (WANT_HM ? NB : 1); ++b) hacc[a][b][0] = hacc[a][b][1] = 0.0;
   double sd[MB], sq[MB], sl[MB], brow[MB];
 #pragma unroll
   for (int mb = 0; mb < MB; ++mb) {
@@ -220,31 +248,33 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
     }
 
     // ---------------- step 2: densities on the accumulator fragments ----------------
-    double psi[WANT_G ? MB : 1][2][2], psd[WANT_H ? MB : 1][2][2];
+    double psi[WANT_G ? MB : 1][2][2], psd[WANT_HM ? MB : 1][2][2];
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
       for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
         for (int pp = 0; pp < 2; ++pp) {
-          double y = acc[mb][nb][pp] - brow[mb];
+          double y = HAS_BIAS ? acc[mb][nb][pp] - brow[mb] : acc[mb][nb][pp];
           const int64_t t = t0 + 8 * nb + 2 * j + pp;
           const bool valid = !partial_tile || (t < p.t_local);
-          if (partial_tile && !valid) y = 0.0;
+          if (partial_tile && !valid) y = 0.0;  // zero-filled columns: harmless for Gr, Hr, Sq (every term has a factor y)
           if (APPLY) {
             acc[mb][nb][pp] = y;
           } else {
-            double f = 0.0, fd = 0.0, ll = 0.0;
-            density_eval<DENS, WANT_G, WANT_L>(y, p.alpha, p.inv_alpha, f, fd, ll);
-            if (partial_tile && !valid) { fd = 0.0; ll = 0.0; }
-            if (WANT_G) { psi[mb][nb][pp] = f; sd[mb] += fd; }
-            if (WANT_H) psd[mb][nb][pp] = fd;
-            if (WANT_L) sl[mb] += ll;
-            sq[mb] = fma(y, y, sq[mb]);
+            double f = 0.0, fd = 0.0, dsd = 0.0, dsl = 0.0;
+            density_eval<DENS, WANT_G, WANT_L>(y, p.dp, tab, f, fd, dsd, dsl);
+            if (valid) {  // psi'(0) and loglik(0) are non-zero: padding columns must not reach Sd and L
+              if (WANT_G) sd[mb] += dsd;
+              if (WANT_L) sl[mb] += dsl;
+            }
+            if (WANT_G) psi[mb][nb][pp] = f;
+            if (WANT_HM) psd[mb][nb][pp] = fd;
+            if (WANT_SQ) sq[mb] = fma(y, y, sq[mb]);
             if (WANT_G) yst[yoff_st + mb * 8 * YP + 8 * nb + 4 * pp] = y;
           }
         }
-    if (APPLY) {
+    if (APPLY || (MODE == PASS_LOSS && p.out != nullptr)) {  // LOSS + out: keep Y' so an accepted try needs no W X product again
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
         const int row = 8 * (MB * warp + mb) + c;
@@ -260,10 +290,21 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
       }
     }
 
-    __syncthreads();  // Y tile complete in shared memory; every warp is done with this X stage
-    if (tid == 0 && it + G::STAGES < my_tiles) {
-      ptx::mbar_expect_tx(&bar[stage], STAGE_BYTES);
-      ptx::tma_load_2d(xs + stage * NP * G::BT, &tmap, (int)((tile0 + (it + G::STAGES) * tstride) * G::BT), 0, &bar[stage]);
+    if (MODE == PASS_LOSS || APPLY) {
+      // no data is exchanged between warps in these modes: no CTA barrier.  Warps drift apart, so one warp's density
+      // evaluation overlaps another's DMMA phase on the shared FP64 pipe; the LAST warp to finish with a stage refills it.
+      ptx::stage_release<G::NWARPS>(&cnt[stage], lane, [&] {
+        if (it + G::STAGES < my_tiles) {
+          ptx::mbar_expect_tx(&bar[stage], STAGE_BYTES);
+          ptx::tma_load_2d(xs + stage * NP * G::BT, &tmap, (int)((tile0 + (it + G::STAGES) * tstride) * G::BT), 0, &bar[stage]);
+        }
+      });
+    } else {
+      __syncthreads();  // Y tile complete in shared memory; every warp is done with this X stage
+      if (tid == 0 && it + G::STAGES < my_tiles) {
+        ptx::mbar_expect_tx(&bar[stage], STAGE_BYTES);
+        ptx::tma_load_2d(xs + stage * NP * G::BT, &tmap, (int)((tile0 + (it + G::STAGES) * tstride) * G::BT), 0, &bar[stage]);
+      }
     }
 
     // ---------------- step 3: G += psi(Y) Y^T, H += psi'(Y) (Y^2)^T (DMMA) ----------------
@@ -276,7 +317,7 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
           const double b = yst[yoff_ld + nbg * 8 * YP + 8 * nbp + 4 * pp];
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb) ptx::dmma(gacc[mb][nbg][0], gacc[mb][nbg][1], psi[mb][nbp][pp], b);
-          if (WANT_H) {
+          if (WANT_HM) {
             const double b2 = b * b;
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) ptx::dmma(hacc[mb][nbg][0], hacc[mb][nbg][1], psd[mb][nbp][pp], b2);
@@ -288,7 +329,7 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
 
   // ---------------- per-CTA partial ----------------
   if (!APPLY) {
-    double* part = p.partial + (size_t)blockIdx.x * pass_partial_size(NP, WANT_G, WANT_H);
+    double* part = p.partial + (size_t)blockIdx.x * pass_partial_size(NP, WANT_G, WANT_HM);
     if (WANT_G) {
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb)
@@ -296,11 +337,11 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
         for (int nbg = 0; nbg < NB; ++nbg) {
           const int row = 8 * (MB * warp + mb) + c, col = 8 * nbg + 2 * j;
           *reinterpret_cast<double2*>(part + row * NP + col) = make_double2(gacc[mb][nbg][0], gacc[mb][nbg][1]);
-          if (WANT_H)
+          if (WANT_HM)
             *reinterpret_cast<double2*>(part + NP * NP + row * NP + col) = make_double2(hacc[mb][nbg][0], hacc[mb][nbg][1]);
         }
     }
-    double* rs = part + (WANT_G ? NP * NP : 0) + (WANT_H ? NP * NP : 0);
+    double* rs = part + (WANT_G ? NP * NP : 0) + (WANT_HM ? NP * NP : 0);
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) {
       double a = sd[mb], b = sq[mb], l = sl[mb];
@@ -311,6 +352,157 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
         const int row = 8 * (MB * warp + mb) + c;
         rs[row] = a; rs[NP + row] = b; rs[2 * NP + row] = l;
       }
+    }
+  }
+}
+
+// =====================================================================================================
+// grady_kernel -- gradient moments from a STORED Y (the accepted line-search try kept by a LOSS pass):
+// Gr = psi(Y) Y^T, Sd [, Hr, Sq] with no W X product (2 N^2 T flop instead of 4 N^2 T).  The TMA tile of Y in
+// shared memory serves both as the source of each warp's own elements (fragment layout, LDS.128) and as the B
+// operand of the DMMA contraction, so there is no staging copy and no CTA barrier: warps are fully decoupled.
+// Sample permutation inside a tile (free: everything is a sum over samples): lane j, half nb', slot pp holds
+// sample 2 (2 j + nb') + pp, i.e. 16-byte chunk 2 j + nb' of the 128-byte row -> with SWIZZLE_128B both the
+// element loads and the B-fragment loads are bank-conflict free.
+// =====================================================================================================
+template <int NP>
+struct GradYGeom {
+  static constexpr int NWARPS = NP >= 64 ? 8 : NP / 8;
+  static constexpr int NTHREADS = NWARPS * 32;
+  static constexpr int MB = NP / (8 * NWARPS);
+  static constexpr int NB = NP / 8;
+  static constexpr int BT = 16;
+  static constexpr int STAGES = 4;
+  static constexpr int MIN_BLOCKS = NP >= 128 ? 1 : (NP == 64 ? 2 : (NP == 32 ? 4 : 8));
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * NP * BT * 8 + (size_t)dmath::TAB_DOUBLES * 8 + 128;
+};
+
+template <int NP, int DENS, bool WANT_H>
+__global__ void __launch_bounds__(GradYGeom<NP>::NTHREADS, GradYGeom<NP>::MIN_BLOCKS)
+grady_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
+  using G = GradYGeom<NP>;
+  constexpr int MB = G::MB, NB = G::NB;
+  constexpr bool NEED_TAB = (DENS == DENS_TANH || DENS == DENS_EXP);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double* ysm = reinterpret_cast<double*>(smem_raw);
+  double* tab = ysm + G::STAGES * NP * G::BT;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tab + dmath::TAB_DOUBLES);
+  int* cnt = reinterpret_cast<int*>(bar + G::STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j = lane & 3, c = lane >> 2;
+  if (NEED_TAB)
+    for (int i = tid; i < dmath::EXP_TAB_N; i += G::NTHREADS) { tab[i] = g_exp_tab[i]; tab[dmath::EXP_TAB_N + i] = g_log_tab[i]; }
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tmap);
+    for (int s = 0; s < G::STAGES; ++s) { ptx::mbar_init(&bar[s], 1); cnt[s] = 0; }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int64_t tile0 = blockIdx.x, tstride = gridDim.x;
+  const int64_t my_tiles = tile0 < p.n_tiles ? (p.n_tiles - tile0 + tstride - 1) / tstride : 0;
+  constexpr uint32_t STAGE_BYTES = NP * G::BT * 8;
+  if (tid == 0) {
+    for (int s = 0; s < G::STAGES && s < my_tiles; ++s) {
+      ptx::mbar_expect_tx(&bar[s], STAGE_BYTES);
+      ptx::tma_load_2d(ysm + s * NP * G::BT, &tmap, (int)((tile0 + s * tstride) * G::BT), 0, &bar[s]);
+    }
+  }
+
+  double gacc[MB][NB][2];
+  double hacc[WANT_H ? MB : 1][WANT_H ? NB : 1][2];
+#pragma unroll
+  for (int a = 0; a < MB; ++a)
+#pragma unroll
+    for (int b = 0; b < NB; ++b) gacc[a][b][0] = gacc[a][b][1] = 0.0;
+#pragma unroll
+  for (int a = 0; a < (WANT_H ? MB : 1); ++a)
+#pragma unroll
+    for (int b = 0; b < (WANT_H ? NB : 1); ++b) hacc[a][b][0] = hacc[a][b][1] = 0.0;
+  double sd[MB], sq[MB];
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb) sd[mb] = sq[mb] = 0.0;
+
+  // lane-constant offsets (doubles): own elements: row 8 (MB warp + mb) + c, chunk (2j + nb') ^ (row & 7) with row & 7 == c
+  int eoff[2], boff[2];
+#pragma unroll
+  for (int nbp = 0; nbp < 2; ++nbp) {
+    eoff[nbp] = (8 * MB * warp + c) * G::BT + (((2 * j + nbp) ^ c) << 1);  // + mb * 8 * BT
+    boff[nbp] = c * G::BT + (((2 * j + nbp) ^ c) << 1);                    // + nbg * 8 * BT
+  }
+
+  for (int64_t it = 0; it < my_tiles; ++it) {
+    const int stage = (int)(it % G::STAGES);
+    const uint32_t parity = (uint32_t)((it / G::STAGES) & 1);
+    const int64_t t0 = (tile0 + it * tstride) * G::BT;
+    const bool partial_tile = (t0 + G::BT > p.t_local);
+    const double* yt = ysm + stage * NP * G::BT;
+    ptx::mbar_wait(&bar[stage], parity);
+
+    double psi[MB][2][2], psd[WANT_H ? MB : 1][2][2];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+      for (int nbp = 0; nbp < 2; ++nbp) {
+        const double2 v = *reinterpret_cast<const double2*>(yt + eoff[nbp] + mb * 8 * G::BT);
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+          const double y = pp ? v.y : v.x;  // out-of-range columns / rows are zero-filled by the TMA unit
+          const int64_t t = t0 + 2 * (2 * j + nbp) + pp;
+          const bool valid = !partial_tile || (t < p.t_local);
+          double f = 0.0, fd = 0.0, dsd = 0.0, dsl = 0.0;
+          density_eval<DENS, true, false>(y, p.dp, tab, f, fd, dsd, dsl);
+          if (valid) sd[mb] += dsd;  // psi'(0) != 0: padding columns must not reach Sd
+          psi[mb][nbp][pp] = f;
+          if (WANT_H) { psd[mb][nbp][pp] = fd; sq[mb] = fma(y, y, sq[mb]); }
+        }
+      }
+#pragma unroll
+    for (int nbp = 0; nbp < 2; ++nbp)
+#pragma unroll
+      for (int nbg = 0; nbg < NB; ++nbg) {
+        const double2 b = *reinterpret_cast<const double2*>(yt + boff[nbp] + nbg * 8 * G::BT);
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          ptx::dmma(gacc[mb][nbg][0], gacc[mb][nbg][1], psi[mb][nbp][0], b.x);
+          ptx::dmma(gacc[mb][nbg][0], gacc[mb][nbg][1], psi[mb][nbp][1], b.y);
+        }
+        if (WANT_H) {
+          const double bx2 = b.x * b.x, by2 = b.y * b.y;
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+            ptx::dmma(hacc[mb][nbg][0], hacc[mb][nbg][1], psd[mb][nbp][0], bx2);
+            ptx::dmma(hacc[mb][nbg][0], hacc[mb][nbg][1], psd[mb][nbp][1], by2);
+          }
+        }
+      }
+    ptx::stage_release<G::NWARPS>(&cnt[stage], lane, [&] {
+      if (it + G::STAGES < my_tiles) {
+        ptx::mbar_expect_tx(&bar[stage], STAGE_BYTES);
+        ptx::tma_load_2d(ysm + stage * NP * G::BT, &tmap, (int)((tile0 + (it + G::STAGES) * tstride) * G::BT), 0, &bar[stage]);
+      }
+    });
+  }
+
+  double* part = p.partial + (size_t)blockIdx.x * pass_partial_size(NP, true, WANT_H);
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+    for (int nbg = 0; nbg < NB; ++nbg) {
+      const int row = 8 * (MB * warp + mb) + c, col = 8 * nbg + 2 * j;
+      *reinterpret_cast<double2*>(part + row * NP + col) = make_double2(gacc[mb][nbg][0], gacc[mb][nbg][1]);
+      if (WANT_H) *reinterpret_cast<double2*>(part + NP * NP + row * NP + col) = make_double2(hacc[mb][nbg][0], hacc[mb][nbg][1]);
+    }
+  double* rs = part + NP * NP + (WANT_H ? NP * NP : 0);
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb) {
+    double a = sd[mb], b = sq[mb];
+    a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+    b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
+    if (j == 0) {
+      const int row = 8 * (MB * warp + mb) + c;
+      rs[row] = a; rs[NP + row] = b; rs[2 * NP + row] = 0.0;
     }
   }
 }

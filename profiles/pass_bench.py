@@ -24,7 +24,8 @@ assert lib.picard_synth_sources(C.c_void_p(x.data_ptr()), C.c_int64(n), C.c_int6
                                 C.c_uint64(42), C.c_int32(0), None) == 0
 w = np.ascontiguousarray(_data.orthogonal(n, 43))
 peak = 37.19
-for mode, name, fl in [(0, "fused", 4.0), (1, "grad", 4.0), (2, "loss", 2.0), (0, "fused+H", 6.0), (1, "grad+H", 6.0)]:
+for mode, name, fl in [(0, "fused", 4.0), (1, "grad", 4.0), (2, "loss", 2.0), (3, "loss+store,gradY", 4.0), (4, "gradY", 2.0),
+                       (0, "fused+H", 6.0), (1, "grad+H", 6.0), (4, "gradY+H", 4.0)]:
     want_h = name.endswith("+H")
     ms = C.c_double()
     err = C.create_string_buffer(512)

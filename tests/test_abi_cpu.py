@@ -41,8 +41,8 @@ def test_abi_version_and_status_strings():
 def test_struct_layouts_match_header_sizes():
     # natural alignment on x86-64: computed by hand from include/picard_b200.h
     assert C.sizeof(_ffi.Config) == 160
-    assert C.sizeof(_ffi.Stats) == 128
-    assert C.sizeof(_ffi.Result) == 88 + 128
+    assert C.sizeof(_ffi.Stats) == 144
+    assert C.sizeof(_ffi.Result) == 88 + 144
 
 
 def test_config_defaults():  # config.rs:64-85

@@ -80,6 +80,18 @@ def test_speculation_does_not_change_the_iterates():
     assert a.stats["fused_passes"] > 0 and b.stats["fused_passes"] == 0
 
 
+def test_y_store_does_not_change_the_iterates():
+    """Serving the gradient of an accepted loss-only try from the stored Y' is an execution strategy only."""
+    x, _, _ = _data.mixture(12, 20_000, seed=3)
+    w0 = _data.orthogonal(12, 43)
+    a = Picard.fit_with_config(x, PicardConfig(w_init=w0, flags=P.FLAG_NO_SPECULATION))
+    b = Picard.fit_with_config(x, PicardConfig(w_init=w0, flags=P.FLAG_NO_SPECULATION | P.FLAG_NO_Y_STORE))
+    assert a.n_iterations == b.n_iterations
+    np.testing.assert_allclose(a.unmixing, b.unmixing, rtol=0, atol=1e-12)
+    assert a.stats["grady_passes"] > 0 and a.stats["grad_passes"] == 0
+    assert b.stats["grady_passes"] == 0 and b.stats["grad_passes"] > 0
+
+
 # ---- the reference's own solver tests (solver.rs:288-408), same assertions ---------------------------
 def _laplace_mix(n, t, seed):
     return _data.mixture(n, t, seed, "laplace")[0]

@@ -40,13 +40,33 @@ def test_pass_modes_agree(n, t):
     full = _gpu.eval_moments(x, w, mode=0, want_h=True)
     grad = _gpu.eval_moments(x, w, mode=1, want_h=True)
     grad_noh = _gpu.eval_moments(x, w, mode=1, want_h=False)
-    loss = _gpu.eval_moments(x, w, mode=2, want_h=False)
+    loss = _gpu.eval_moments(x, w, mode=2, want_h=True)   # LOSS mode: want_h asks for the Sq row sums only
+    loss_nosq = _gpu.eval_moments(x, w, mode=2, want_h=False)
     for k in ("gr", "sd", "hr", "sq"):
         np.testing.assert_allclose(grad[k], full[k], rtol=1e-13, atol=1e-9)
-    for k in ("gr", "sd", "sq"):
+    for k in ("gr", "sd"):  # Sq is only produced with want_h (it feeds the non-ortho Hessian / loss)
         np.testing.assert_allclose(grad_noh[k], full[k], rtol=1e-13, atol=1e-9)
     for k in ("sq", "lrow"):
         np.testing.assert_allclose(loss[k], full[k], rtol=1e-13, atol=1e-9)
+    np.testing.assert_allclose(loss_nosq["lrow"], full["lrow"], rtol=1e-13, atol=1e-9)
+
+
+@pytest.mark.parametrize("n,t", [(3, 1000), (16, 5003), (40, 2000), (64, 4097), (128, 2050)])
+@pytest.mark.parametrize("kind,alpha", [(orc.TANH, 1.0), (orc.EXP, 0.1), (orc.CUBE, 1.0)])
+def test_stored_y_gradient_path_matches_oracle(n, t, kind, alpha):
+    """mode 3: a loss-only pass that stores Y' followed by the gradient moments computed from the stored Y'
+    (what an accepted loss-only line-search try costs) gives the same moments as the oracle."""
+    x = _data.whitened(n, t, seed=n + 17)
+    w = _data.orthogonal(n, seed=n + 2) + 0.03 * np.random.default_rng(n).standard_normal((n, n))
+    ref = _ref(x, w, kind, alpha)
+    for want_h in (True, False):
+        got = _gpu.eval_moments(x, w, kind, alpha, mode=3, want_h=want_h)
+        assert _data.rel_err(got["gr"], ref.gr) <= TOL
+        assert _data.rel_err(got["sd"], ref.sd) <= TOL
+        assert _data.rel_err(got["lrow"], ref.lrow) <= TOL
+        if want_h:
+            assert _data.rel_err(got["hr"], ref.hr) <= TOL
+            assert _data.rel_err(got["sq"], ref.sq) <= TOL
 
 
 def test_identity_w_is_default():

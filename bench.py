@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-t", type=int, default=100_000, help="samples of the CPU-baseline sample")
     ap.add_argument("--cpu-iters", type=int, default=6, help="outer iterations of the CPU-baseline sample")
+    ap.add_argument("--flags", type=int, default=0, help="PICARD_FLAG_* bits (ablation)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -222,7 +223,7 @@ def main():
     torch.cuda.synchronize()
 
     cfg = P.PicardConfig(density=P.Tanh(wl["alpha"]) if wl["kind"] == 0 else (P.Exp(wl["alpha"]) if wl["kind"] == 1 else P.Cube()),
-                         ortho=wl["ortho"], extended=wl["extended"], comm=comm, device=local_rank)
+                         ortho=wl["ortho"], extended=wl["extended"], comm=comm, device=local_rank, flags=args.flags)
     core = P.CoreLoop(x1_dev[:, :t_local], cfg, covariance_identity=wl["extended"])
 
     def run_iters(k_iters):
@@ -259,7 +260,7 @@ def main():
     # ---- roofline of the dominant kernel: the fused pass (falls back to grad / loss variants if none ran)
     n2t = float(n) * n * t_local
     cand = [("fused", 4.0 * n2t, d["fused_passes"], d["pass_ms_fused"]), ("grad", 4.0 * n2t, d["grad_passes"], d["pass_ms_grad"]),
-            ("loss", 2.0 * n2t, d["loss_passes"], d["pass_ms_loss"])]
+            ("loss", 2.0 * n2t, d["loss_passes"], d["pass_ms_loss"]), ("grady", 2.0 * n2t, d["grady_passes"], d["pass_ms_grady"])]
     cand = [c for c in cand if c[2] > 0 and c[3] > 0]
     roof = None
     if cand:
@@ -272,8 +273,8 @@ def main():
                 "(profiles/microbench/fp64_pipes_r01.jsonl); MEASURED_PEAKS.json has no FP64 entry",
                 "share_of_step": ms / dev_ms, "hbm_gbs": 8.0 * n * t_local / (avg_ms * 1e-3) / 1e9}
     pass_mix = {"fused": d["fused_passes"], "grad": d["grad_passes"], "loss": d["loss_passes"], "ls_tries": d["ls_tries"],
-                "fallbacks": d["fallbacks"], "sign_changes": d["sign_changes"], "restarts": restarts,
-                "pass_ms": {"fused": d["pass_ms_fused"], "grad": d["pass_ms_grad"], "loss": d["pass_ms_loss"]}}
+                "fallbacks": d["fallbacks"], "sign_changes": d["sign_changes"], "restarts": restarts, "grady": d["grady_passes"],
+                "pass_ms": {"fused": d["pass_ms_fused"], "grad": d["pass_ms_grad"], "loss": d["pass_ms_loss"], "grady": d["pass_ms_grady"]}}
     state = core.state()
     core.close()
     del x1_dev

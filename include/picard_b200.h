@@ -69,8 +69,9 @@ typedef struct {
   uint32_t flags;         /* PICARD_FLAG_* */
 } picard_config_t;
 
-#define PICARD_FLAG_NO_SPECULATION 1u /* line-search tries never carry the gradient moments (debug / ablation) */
+#define PICARD_FLAG_NO_SPECULATION 1u /* never run the speculative fused first try (it is only used when there is no Y store) */
 #define PICARD_FLAG_KEEP_SOURCES_ON_DEVICE 2u /* picard_fit_device: do not copy `sources` to the host */
+#define PICARD_FLAG_FORCE_SPECULATION 8u /* speculative fused first try even though the Y store is available (ablation) */
 #define PICARD_FLAG_NO_Y_STORE 4u /* loss-only tries do not keep Y' (saves one N x T buffer; the gradient recomputes W X) */
 
 /* Measurement record filled by every fit / core run (not in the reference). */

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpicard_b200.so")
+LIB_PATH = os.environ.get("PICARD_B200_LIB") or os.path.join(_HERE, "libpicard_b200.so")  # env override: profiling builds only
 
 dp = C.POINTER(C.c_double)
 
@@ -58,6 +58,7 @@ class Result(C.Structure):  # picard_result_t
 FLAG_NO_SPECULATION = 1
 FLAG_KEEP_SOURCES_ON_DEVICE = 2
 FLAG_NO_Y_STORE = 4
+FLAG_FORCE_SPECULATION = 8
 UNIQUE_ID_BYTES = 128
 
 _lib = None

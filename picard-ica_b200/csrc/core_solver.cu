@@ -161,7 +161,12 @@ void CoreSolver::try_point(double alpha, bool speculate) {
 
 int64_t CoreSolver::run(int64_t max_new) {
   const int n = dims_.n;
-  const bool no_spec = (cfg_.flags & PICARD_FLAG_NO_SPECULATION) != 0;
+  // Line-search policy.  With the Y store every try is a LOSS pass that keeps Y' (2 N^2 T flop) and only an ACCEPTED try
+  // pays for the gradient moments (stored-Y pass, 2 N^2 T): nothing is ever computed for a rejected point.  Without the
+  // store (no memory / flag) the first try of an iteration speculatively runs the FUSED pass instead.
+  const bool can_fuse = pass_padded_size(n) <= 128;
+  const bool force_spec = (cfg_.flags & PICARD_FLAG_FORCE_SPECULATION) != 0 && can_fuse;
+  const bool no_spec = (cfg_.flags & PICARD_FLAG_NO_SPECULATION) != 0 || !can_fuse || (ybuf_.p != nullptr && !force_spec);
   PICARD_CUDA(cudaEventRecord(ev_run0_, st_));
   if (!started_) {
     // initial loss with signs = 1 (core.rs:185-194, quirk Q1); the same pass already yields the first gradient
@@ -284,7 +289,12 @@ void CoreSolver::hook_point(const double* w_host, const double* c_host, const do
   if (c_host) PICARD_CUDA(cudaMemcpyAsync(C_, c_host, sizeof(double) * nn, cudaMemcpyHostToDevice, st_));
   if (old_signs_host) PICARD_CUDA(cudaMemcpyAsync(old_signs_, old_signs_host, sizeof(double) * n, cudaMemcpyHostToDevice, st_));
   if (!dims_.ortho) stats_.kernel_launches += small::sln_det(W_, n, lu_work_, mom_cur_ + mom_size(n), st_);
-  eval_pass(W_, PASS_FUSED, need_h_, dens_, alpha_, mom_cur_);
+  if (ybuf_.p) {  // the product path: LOSS pass keeping Y', then the stored-Y gradient pass
+    eval_pass(W_, PASS_LOSS, need_h_, dens_, alpha_, mom_cur_, true);
+    eval_pass(W_, PASS_GRADY, need_h_, dens_, alpha_, mom_cur_);
+  } else {
+    eval_pass(W_, PASS_FUSED, need_h_, dens_, alpha_, mom_cur_);
+  }
   small::FrontArgs fa;
   fa.d = dims_; fa.mom = mom_cur_; fa.C = C_; fa.G = G_; fa.Gtmp = Gtmp_; fa.G_old = Gold_; fa.H = H_; fa.hoff = hoff_;
   fa.signs = signs_; fa.old_signs = old_signs_; fa.S_prev = Sprev_; fa.mem_s = mem_s_; fa.mem_y = mem_y_; fa.mem_r = mem_r_;

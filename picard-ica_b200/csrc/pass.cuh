@@ -356,190 +356,6 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
   }
 }
 
-// =====================================================================================================
-// grady_kernel -- gradient moments from a STORED Y (the accepted line-search try kept by a LOSS pass):
-// Gr = psi(Y) Y^T, Sd [, Hr, Sq] with no W X product (2 N^2 T flop instead of 4 N^2 T).  The TMA tile of Y in
-// shared memory serves both as the source of each warp's own elements (fragment layout, LDS.128) and as the B
-// operand of the DMMA contraction, so there is no staging copy and no CTA barrier: warps are fully decoupled.
-// Sample permutation inside a tile (free: everything is a sum over samples): lane j, half nb', slot pp holds
-// sample 2 (2 j + nb') + pp, i.e. 16-byte chunk 2 j + nb' of the 128-byte row -> with SWIZZLE_128B both the
-// element loads and the B-fragment loads are bank-conflict free.
-// =====================================================================================================
-template <int NP>
-struct GradYGeom {
-  static constexpr int NWARPS = NP >= 64 ? 8 : NP / 8;
-  static constexpr int NTHREADS = NWARPS * 32;
-  static constexpr int MB = NP / (8 * NWARPS);
-  static constexpr int NB = NP / 8;
-  static constexpr int BT = 16;
-  static constexpr int STAGES = 4;
-  static constexpr int MIN_BLOCKS = NP >= 128 ? 1 : (NP == 64 ? 2 : (NP == 32 ? 4 : 8));
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * NP * BT * 8 + (size_t)dmath::TAB_DOUBLES * 8 + 128;
-};
-
-template <int NP, int DENS, bool WANT_H>
-__global__ void __launch_bounds__(GradYGeom<NP>::NTHREADS, GradYGeom<NP>::MIN_BLOCKS)
-grady_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
-  using G = GradYGeom<NP>;
-  constexpr int MB = G::MB, NB = G::NB;
-  constexpr bool NEED_TAB = (DENS == DENS_TANH || DENS == DENS_EXP);
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  double* ysm = reinterpret_cast<double*>(smem_raw);
-  double* tab = ysm + G::STAGES * NP * G::BT;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(tab + dmath::TAB_DOUBLES);
-  int* cnt = reinterpret_cast<int*>(bar + G::STAGES);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int j = lane & 3, c = lane >> 2;
-  if (NEED_TAB)
-    for (int i = tid; i < dmath::EXP_TAB_N; i += G::NTHREADS) { tab[i] = g_exp_tab[i]; tab[dmath::EXP_TAB_N + i] = g_log_tab[i]; }
-  if (tid == 0) {
-    ptx::prefetch_tmap(&tmap);
-    for (int s = 0; s < G::STAGES; ++s) { ptx::mbar_init(&bar[s], 1); cnt[s] = 0; }
-    ptx::fence_barrier_init();
-  }
-  __syncthreads();
-
-  const int64_t tile0 = blockIdx.x, tstride = gridDim.x;
-  const int64_t my_tiles = tile0 < p.n_tiles ? (p.n_tiles - tile0 + tstride - 1) / tstride : 0;
-  constexpr uint32_t STAGE_BYTES = NP * G::BT * 8;
-  if (tid == 0) {
-    for (int s = 0; s < G::STAGES && s < my_tiles; ++s) {
-      ptx::mbar_expect_tx(&bar[s], STAGE_BYTES);
-      ptx::tma_load_2d(ysm + s * NP * G::BT, &tmap, (int)((tile0 + s * tstride) * G::BT), 0, &bar[s]);
-    }
-  }
-
-  double gacc[MB][NB][2];
-  double hacc[WANT_H ? MB : 1][WANT_H ? NB : 1][2];
-#pragma unroll
-  for (int a = 0; a < MB; ++a)
-#pragma unroll
-    for (int b = 0; b < NB; ++b) gacc[a][b][0] = gacc[a][b][1] = 0.0;
-#pragma unroll
-  for (int a = 0; a < (WANT_H ? MB : 1); ++a)
-#pragma unroll
-    for (int b = 0; b < (WANT_H ? NB : 1); ++b) hacc[a][b][0] = hacc[a][b][1] = 0.0;
-  double sd[MB], sq[MB];
-#pragma unroll
-  for (int mb = 0; mb < MB; ++mb) sd[mb] = sq[mb] = 0.0;
-
-  // lane-constant offsets (doubles): own elements: row 8 (MB warp + mb) + c, chunk (2j + nb') ^ (row & 7) with row & 7 == c
-  int eoff[2], boff[2];
-#pragma unroll
-  for (int nbp = 0; nbp < 2; ++nbp) {
-    eoff[nbp] = (8 * MB * warp + c) * G::BT + (((2 * j + nbp) ^ c) << 1);  // + mb * 8 * BT
-    boff[nbp] = c * G::BT + (((2 * j + nbp) ^ c) << 1);                    // + nbg * 8 * BT
-  }
-
-  for (int64_t it = 0; it < my_tiles; ++it) {
-    const int stage = (int)(it % G::STAGES);
-    const uint32_t parity = (uint32_t)((it / G::STAGES) & 1);
-    const int64_t t0 = (tile0 + it * tstride) * G::BT;
-    const bool partial_tile = (t0 + G::BT > p.t_local);
-    const double* yt = ysm + stage * NP * G::BT;
-    ptx::mbar_wait(&bar[stage], parity);
-
-    double psi[MB][2][2], psd[WANT_H ? MB : 1][2][2];
-#pragma unroll
-    for (int mb = 0; mb < MB; ++mb)
-#pragma unroll
-      for (int nbp = 0; nbp < 2; ++nbp) {
-        const double2 v = *reinterpret_cast<const double2*>(yt + eoff[nbp] + mb * 8 * G::BT);
-#pragma unroll
-        for (int pp = 0; pp < 2; ++pp) {
-          const double y = pp ? v.y : v.x;  // out-of-range columns / rows are zero-filled by the TMA unit
-          const int64_t t = t0 + 2 * (2 * j + nbp) + pp;
-          const bool valid = !partial_tile || (t < p.t_local);
-          double f = 0.0, fd = 0.0, dsd = 0.0, dsl = 0.0;
-          density_eval<DENS, true, false>(y, p.dp, tab, f, fd, dsd, dsl);
-          if (valid) sd[mb] += dsd;  // psi'(0) != 0: padding columns must not reach Sd
-          psi[mb][nbp][pp] = f;
-          if (WANT_H) { psd[mb][nbp][pp] = fd; sq[mb] = fma(y, y, sq[mb]); }
-        }
-      }
-#pragma unroll
-    for (int nbp = 0; nbp < 2; ++nbp)
-#pragma unroll
-      for (int nbg = 0; nbg < NB; ++nbg) {
-        const double2 b = *reinterpret_cast<const double2*>(yt + boff[nbp] + nbg * 8 * G::BT);
-#pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {
-          ptx::dmma(gacc[mb][nbg][0], gacc[mb][nbg][1], psi[mb][nbp][0], b.x);
-          ptx::dmma(gacc[mb][nbg][0], gacc[mb][nbg][1], psi[mb][nbp][1], b.y);
-        }
-        if (WANT_H) {
-          const double bx2 = b.x * b.x, by2 = b.y * b.y;
-#pragma unroll
-          for (int mb = 0; mb < MB; ++mb) {
-            ptx::dmma(hacc[mb][nbg][0], hacc[mb][nbg][1], psd[mb][nbp][0], bx2);
-            ptx::dmma(hacc[mb][nbg][0], hacc[mb][nbg][1], psd[mb][nbp][1], by2);
-          }
-        }
-      }
-    ptx::stage_release<G::NWARPS>(&cnt[stage], lane, [&] {
-      if (it + G::STAGES < my_tiles) {
-        ptx::mbar_expect_tx(&bar[stage], STAGE_BYTES);
-        ptx::tma_load_2d(ysm + stage * NP * G::BT, &tmap, (int)((tile0 + (it + G::STAGES) * tstride) * G::BT), 0, &bar[stage]);
-      }
-    });
-  }
-
-  double* part = p.partial + (size_t)blockIdx.x * pass_partial_size(NP, true, WANT_H);
-#pragma unroll
-  for (int mb = 0; mb < MB; ++mb)
-#pragma unroll
-    for (int nbg = 0; nbg < NB; ++nbg) {
-      const int row = 8 * (MB * warp + mb) + c, col = 8 * nbg + 2 * j;
-      *reinterpret_cast<double2*>(part + row * NP + col) = make_double2(gacc[mb][nbg][0], gacc[mb][nbg][1]);
-      if (WANT_H) *reinterpret_cast<double2*>(part + NP * NP + row * NP + col) = make_double2(hacc[mb][nbg][0], hacc[mb][nbg][1]);
-    }
-  double* rs = part + NP * NP + (WANT_H ? NP * NP : 0);
-#pragma unroll
-  for (int mb = 0; mb < MB; ++mb) {
-    double a = sd[mb], b = sq[mb];
-    a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
-    b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
-    if (j == 0) {
-      const int row = 8 * (MB * warp + mb) + c;
-      rs[row] = a; rs[NP + row] = b; rs[2 * NP + row] = 0.0;
-    }
-  }
-}
-
-// Sum the per-CTA partials in a fixed order into the compact moment buffer (ld = n).  Sections a mode does
-// not produce are left untouched.
-static __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n_parts, int np, int n, int want_g, int want_h,
-                                       int want_l, double* __restrict__ mom) {
-  const int psz = pass_partial_size(np, want_g, want_h);
-  const int64_t nn = (int64_t)n * n;
-  const int64_t total = (want_g ? nn : 0) + (want_h ? nn : 0) + 3 * (int64_t)n;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = e;
-    int src;
-    int64_t dst;
-    bool skip = false;
-    if (want_g && r < nn) { src = (int)(r / n) * np + (int)(r % n); dst = mom_off_gr(n) + r; }
-    else {
-      if (want_g) r -= nn;
-      if (want_h && r < nn) { src = np * np + (int)(r / n) * np + (int)(r % n); dst = mom_off_hr(n) + r; }
-      else {
-        if (want_h) r -= nn;
-        const int base = (want_g ? np * np : 0) + (want_h ? np * np : 0);
-        const int sec = (int)(r / n), i = (int)(r % n);
-        src = base + sec * np + i;
-        dst = (sec == 0 ? mom_off_sd(n) : (sec == 1 ? mom_off_sq(n) : mom_off_ll(n))) + i;
-        if (sec == 0 && !want_g) skip = true;
-        if (sec == 2 && !want_l) skip = true;
-      }
-    }
-    if (skip) continue;
-    double s = 0.0;
-    for (int k = 0; k < n_parts; ++k) s += partial[(size_t)k * psz + src];
-    mom[dst] = s;
-  }
-}
-
 // ---- host-side launch description
 struct PassLaunch {
   const double* d_x;     // (n_in x t_local), leading dimension ldx (even), device, 16-byte aligned
@@ -564,5 +380,10 @@ size_t pass_workspace_doubles(int n, int sm_count);  // partial workspace needed
 
 template <int NP>
 int launch_pass_np(const PassLaunch& L, const CUtensorMap& tmap);
+// row-block kernels (rowblock.cuh): LOSS / APPLY with W fragments in registers (KP = 128, 256) and the stored-Y gradient
+template <int KP>
+int launch_rb_loss(const PassLaunch& L, const CUtensorMap& tmap);
+template <int NP>
+int launch_rb_grady(const PassLaunch& L, const CUtensorMap& tmap);
 
 }  // namespace picard

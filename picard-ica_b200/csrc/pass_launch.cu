@@ -7,15 +7,17 @@ namespace picard {
 
 int pass_padded_size(int n) {
   if (n <= 0) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
-  for (int np : {8, 16, 32, 64, 128})
+  for (int np : {8, 16, 32, 64, 128, 256})
     if (n <= np) return np;
-  throw Error(PICARD_INVALID_DIMENSIONS,
-              "Invalid dimensions: more than 128 components are not supported by this build of the fused pass");
+  throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: more than 256 components / features are not supported by this build");
 }
 
 size_t pass_workspace_doubles(int n, int sm_count) {
   const int np = pass_padded_size(n);
-  return (size_t)sm_count * PASS_MAX_BLOCKS_PER_SM * (size_t)pass_partial_size(np, true, true);
+  // per-CTA partials: the fused / grad kernels write NP x NP (x2 with H) per CTA, the row-block kernels RP x NP
+  if (np <= 64) return (size_t)sm_count * PASS_MAX_BLOCKS_PER_SM * (size_t)pass_partial_size(np, true, true);
+  if (np == 128) return (size_t)sm_count * 2 * (size_t)pass_partial_size(128, true, true);
+  return (size_t)sm_count * 2 * (size_t)(2 * 64 * 256 + 3 * 256);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -60,6 +62,23 @@ int launch_pass(const PassLaunch& L) {
   const int nmax = L.n_in > L.n_out ? L.n_in : L.n_out;
   const int np = pass_padded_size(nmax);
   CUtensorMap tmap = make_tmap(L.d_x, L.ldx, L.t_local, L.n_in, np);
+  // Gram-type passes read their input as "Y": the stored-Y gradient pass, and psi(y) = y (covariance of the whitening step,
+  // C = Y Y^T / T of core.rs:202)
+  if (L.mode == PASS_GRADY || (L.mode == PASS_GRAD && L.dens == DENS_LINEAR)) {
+    switch (np) {
+      case 8: return launch_rb_grady<8>(L, tmap);
+      case 16: return launch_rb_grady<16>(L, tmap);
+      case 32: return launch_rb_grady<32>(L, tmap);
+      case 64: return launch_rb_grady<64>(L, tmap);
+      case 128: return launch_rb_grady<128>(L, tmap);
+      default: return launch_rb_grady<256>(L, tmap);
+    }
+  }
+  if ((L.mode == PASS_LOSS || L.mode == PASS_APPLY) && np >= 128)
+    return np == 128 ? launch_rb_loss<128>(L, tmap) : launch_rb_loss<256>(L, tmap);
+  if (np > 128)
+    throw Error(PICARD_COMPUTATION_ERROR, "Computation error: N > 128 needs the Y store (the from-X gradient kernels hold N x N accumulators "
+                                          "in one SM's registers); do not set PICARD_FLAG_NO_Y_STORE / free some device memory");
   switch (np) {
     case 8: return launch_pass_np<8>(L, tmap);
     case 16: return launch_pass_np<16>(L, tmap);

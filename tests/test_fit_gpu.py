@@ -69,27 +69,43 @@ def test_cube_density_subgaussian():
     _cmp(res, ref)
 
 
-def test_speculation_does_not_change_the_iterates():
-    """The speculative fused try is an execution strategy only: same iterate sequence with it disabled."""
-    x, _, _ = _data.mixture(10, 20_000, seed=2)
-    w0 = _data.orthogonal(10, 43)
-    a = Picard.fit_with_config(x, PicardConfig(w_init=w0))
-    b = Picard.fit_with_config(x, PicardConfig(w_init=w0, flags=P.FLAG_NO_SPECULATION))
-    assert a.n_iterations == b.n_iterations
-    np.testing.assert_allclose(a.unmixing, b.unmixing, rtol=0, atol=1e-12)
-    assert a.stats["fused_passes"] > 0 and b.stats["fused_passes"] == 0
+@pytest.mark.parametrize("n", [10, 100])
+def test_execution_strategies_do_not_change_the_iterates(n):
+    """Y store (default), speculative fused first try, and plain loss + from-X gradient passes are execution
+    strategies only: same iterate sequence, different pass mix."""
+    x, _, _ = _data.mixture(n, 20_000, seed=2)
+    w0 = _data.orthogonal(n, 43)
+    kw = dict(w_init=w0, max_iter=40)
+    a = Picard.fit_with_config(x, PicardConfig(**kw))                                                    # LOSS + Y store, stored-Y gradient
+    b = Picard.fit_with_config(x, PicardConfig(flags=P.FLAG_FORCE_SPECULATION, **kw))                   # speculative fused first try
+    c = Picard.fit_with_config(x, PicardConfig(flags=P.FLAG_NO_Y_STORE, **kw))                          # no store: speculation + from-X gradient
+    d = Picard.fit_with_config(x, PicardConfig(flags=P.FLAG_NO_Y_STORE | P.FLAG_NO_SPECULATION, **kw))  # loss-only tries + from-X gradient
+    for r in (b, c, d):
+        assert r.n_iterations == a.n_iterations
+        np.testing.assert_allclose(r.unmixing, a.unmixing, rtol=0, atol=1e-11)
+    assert a.stats["fused_passes"] == 0 and a.stats["grad_passes"] == 0 and a.stats["grady_passes"] > 0
+    assert b.stats["fused_passes"] > 0
+    assert c.stats["fused_passes"] > 0 and c.stats["grady_passes"] == 0
+    assert d.stats["fused_passes"] == 0 and d.stats["grady_passes"] == 0 and d.stats["grad_passes"] > 0
 
 
-def test_y_store_does_not_change_the_iterates():
-    """Serving the gradient of an accepted loss-only try from the stored Y' is an execution strategy only."""
-    x, _, _ = _data.mixture(12, 20_000, seed=3)
-    w0 = _data.orthogonal(12, 43)
-    a = Picard.fit_with_config(x, PicardConfig(w_init=w0, flags=P.FLAG_NO_SPECULATION))
-    b = Picard.fit_with_config(x, PicardConfig(w_init=w0, flags=P.FLAG_NO_SPECULATION | P.FLAG_NO_Y_STORE))
-    assert a.n_iterations == b.n_iterations
-    np.testing.assert_allclose(a.unmixing, b.unmixing, rtol=0, atol=1e-12)
-    assert a.stats["grady_passes"] > 0 and a.stats["grad_passes"] == 0
-    assert b.stats["grady_passes"] == 0 and b.stats["grad_passes"] > 0
+def test_n_above_128_fit():
+    """N = 160 (row-block kernels, eigh-based whitening of 160 features): Picard-O extended against the oracle."""
+    x, a, _ = _data.mixture(160, 40_000, seed=9, kind="mixed")
+    w0 = _data.orthogonal(160, 43)
+    res = Picard.fit_with_config(x, PicardConfig(w_init=w0, max_iter=60))
+    ref = orc.fit(x, orc.Config(w_init=w0, max_iter=60))
+    _cmp(res, ref)
+
+
+def test_n_above_128_nonortho_exp():
+    """BASELINE configs[3] in miniature at N > 128: non-ortho, exp(alpha = 0.1), Laplace sources, H from the stored Y'."""
+    x, a, _ = _data.mixture(136, 30_000, seed=11, kind="laplace")
+    w0 = _data.orthogonal(136, 43)
+    cfg = dict(ortho=False, extended=False, w_init=w0, max_iter=25)
+    res = Picard.fit_with_config(x, PicardConfig(density=DensityType.exp_with_alpha(0.1), **cfg))
+    ref = orc.fit(x, orc.Config(density=orc.EXP, alpha=0.1, **cfg))
+    _cmp(res, ref)
 
 
 # ---- the reference's own solver tests (solver.rs:288-408), same assertions ---------------------------

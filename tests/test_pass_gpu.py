@@ -69,6 +69,31 @@ def test_stored_y_gradient_path_matches_oracle(n, t, kind, alpha):
             assert _data.rel_err(got["sq"], ref.sq) <= TOL
 
 
+@pytest.mark.parametrize("n,t", [(130, 1500), (200, 2001), (256, 1040)])
+@pytest.mark.parametrize("kind,alpha", [(orc.TANH, 1.0), (orc.EXP, 0.1)])
+def test_n_above_128_row_block_kernels(n, t, kind, alpha):
+    """N in (128, 256]: the row-block partitioned LOSS (+ Y store) and stored-Y gradient kernels (BASELINE configs[3] is N = 256)."""
+    x = _data.whitened(n, t, seed=n)
+    w = _data.orthogonal(n, seed=n + 2) + 0.02 * np.random.default_rng(n).standard_normal((n, n))
+    ref = _ref(x, w, kind, alpha)
+    loss = _gpu.eval_moments(x, w, kind, alpha, mode=2, want_h=True)
+    assert _data.rel_err(loss["lrow"], ref.lrow) <= TOL and _data.rel_err(loss["sq"], ref.sq) <= TOL
+    for want_h in (True, False):
+        got = _gpu.eval_moments(x, w, kind, alpha, mode=3, want_h=want_h)
+        assert _data.rel_err(got["gr"], ref.gr) <= TOL
+        assert _data.rel_err(got["sd"], ref.sd) <= TOL
+        assert _data.rel_err(got["lrow"], ref.lrow) <= TOL
+        if want_h:
+            assert _data.rel_err(got["hr"], ref.hr) <= TOL
+            assert _data.rel_err(got["sq"], ref.sq) <= TOL
+
+
+def test_from_x_gradient_kernels_refuse_n_above_128():
+    x = np.random.default_rng(0).standard_normal((140, 500))
+    with pytest.raises(RuntimeError, match="N > 128 needs the Y store"):
+        _gpu.eval_moments(x, None, mode=0, want_h=False)
+
+
 def test_identity_w_is_default():
     x = _data.whitened(6, 999, seed=2)
     a = _gpu.eval_moments(x, None)

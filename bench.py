@@ -267,7 +267,7 @@ def main():
         name, flops, cnt, ms = max(cand, key=lambda c: c[3])
         avg_ms = ms / cnt
         ach = flops / (avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": f"pass_kernel<{name}>", "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+        roof = {"bound": "tensor", "kernel": {"loss": "rb_loss_kernel (LOSS + Y store)", "grady": "rb_grady_kernel (stored-Y gradient)"}.get(name, f"pass_kernel<{name}>"), "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": ach / FP64_PEAK_TFLOPS, "traffic": None, "avg_launch_ms": avg_ms, "launches": cnt,
                 "flops_per_launch": flops, "peak_source": "FP64 DMMA m8n8k4 microbenchmark measured by us "
                 "(profiles/microbench/fp64_pipes_r01.jsonl); MEASURED_PEAKS.json has no FP64 entry",

@@ -296,13 +296,28 @@ def _invert_matrix(m: np.ndarray):
     return aug[:, n:].copy()
 
 
+def _adopt(ptr, shape):
+    """Wrap a library-owned buffer as an ndarray WITHOUT copying (sources can be tens of GB); the buffer is released
+    through picard_result_free when the array and every view of it are gone."""
+    import weakref
+    a = np.ctypeslib.as_array(ptr, shape=shape)
+    holder = _ffi.Result()
+    holder.sources = ptr  # picard_result_free frees every non-null member: a result holding only this buffer
+    weakref.finalize(a, lambda h=holder: _ffi.lib().picard_result_free(C.byref(h)))
+    return a
+
+
 def _from_c_result(r: _ffi.Result) -> PicardResult:
     nc, nf, t = r.n_components, r.n_features, r.n_samples
 
     def arr(ptr, shape):
         return np.ctypeslib.as_array(ptr, shape=shape).copy() if ptr else None
 
-    out = PicardResult(arr(r.whitening, (nc, nf)), arr(r.unmixing, (nc, nc)), arr(r.sources, (nc, t)), arr(r.mean, (nf,)),
+    sources = None
+    if r.sources:
+        sources = _adopt(r.sources, (nc, t))
+        r.sources = None  # ownership moved to the ndarray
+    out = PicardResult(arr(r.whitening, (nc, nf)), arr(r.unmixing, (nc, nc)), sources, arr(r.mean, (nf,)),
                        int(r.n_iterations), bool(r.converged), float(r.gradient_norm), arr(r.signs, (nc,)), r.stats.as_dict())
     _ffi.lib().picard_result_free(C.byref(r))
     return out

@@ -289,23 +289,29 @@ def main():
         torch.cuda.empty_cache()
         xh = x_host.numpy()
         cfg2 = P.PicardConfig(density=cfg.density, ortho=wl["ortho"], extended=wl["extended"], w_init=w0, comm=comm, device=local_rank)
-        barrier()
-        e_t0 = time.perf_counter()
-        res = P.Picard.fit_with_config(xh, cfg2)
-        gn = float(res.gradient_norm)  # result read on the host
-        barrier()
-        e_s = time.perf_counter() - e_t0
-        te = torch.tensor([e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e_s = float(te[0])
-        e2e = {"value": res.n_iterations / e_s, "unit": UNIT, "h2d_bytes_per_step": res.stats["h2d_bytes"] / max(res.n_iterations, 1),
-               "d2h_bytes_per_step": res.stats["d2h_bytes"] / max(res.n_iterations, 1), "iterations": res.n_iterations,
-               "converged": bool(res.converged), "gradient_norm": gn, "seconds": e_s, "core_ms": res.stats["core_ms"],
-               "preprocess_ms": res.stats["preprocess_ms"], "h2d_ms": res.stats["h2d_ms"], "d2h_ms": res.stats["d2h_ms"],
+        runs = []
+        for _rep in range(3):  # three complete calls; the median is reported, all three are listed
+            res = None
+            barrier()
+            e_t0 = time.perf_counter()
+            res = P.Picard.fit_with_config(xh, cfg2)
+            gn = float(res.gradient_norm)  # result read on the host
+            chk = float(res.sources[0, 0]) + float(res.sources[-1, -1])  # the sources are on the host
+            barrier()
+            e_s = time.perf_counter() - e_t0
+            te = torch.tensor([e_s], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            runs.append((float(te[0]), res.stats, res.n_iterations, bool(res.converged), gn))
+        runs.sort(key=lambda r: r[0])
+        e_s, st_e, n_it_e, conv_e, gn = runs[1]
+        e2e = {"value": n_it_e / e_s, "unit": UNIT, "h2d_bytes_per_step": st_e["h2d_bytes"] / max(n_it_e, 1),
+               "d2h_bytes_per_step": st_e["d2h_bytes"] / max(n_it_e, 1), "iterations": n_it_e,
+               "converged": conv_e, "gradient_norm": gn, "seconds": e_s, "seconds_all_runs": [r[0] for r in runs],
+               "core_ms": st_e["core_ms"], "preprocess_ms": st_e["preprocess_ms"], "h2d_ms": st_e["h2d_ms"], "d2h_ms": st_e["d2h_ms"],
                "what": "Picard.fit_with_config on pinned host X (this rank's shard): H2D, centering, whitening, fit to convergence, "
-                       "D2H of sources; iterations / wall seconds"}
-        del res
+                       "D2H of sources; iterations / wall seconds (median of 3 calls)"}
+        del res, runs
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

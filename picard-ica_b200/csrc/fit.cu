@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cmath>
 #include <random>
+#include <mutex>
 #include <thread>
 
 #include "engine.cuh"
@@ -82,6 +83,15 @@ int apply_device(const double* a_host, const double* mean_host, int n_out, int n
 void center_whiten_device(const double* d_x, int nf, int64_t t_local, int64_t ldx, int nc, bool centering, bool whiten,
                           picard_comm* comm, int sm_count, cudaStream_t st, std::vector<double>& mean_host,
                           std::vector<double>& k_host, double t_total, picard_stats_t* stats) {
+  const bool tr = getenv("PICARD_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!tr) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[picard trace]   %-26s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t_prev).count());
+    t_prev = t1;
+  };
   mean_host.clear();
   k_host.clear();
   DevBuf<double> dmean((size_t)nf);
@@ -96,6 +106,7 @@ void center_whiten_device(const double* d_x, int nf, int64_t t_local, int64_t ld
     for (int i = 0; i < nf; ++i) mean_host[i] /= t_total;
     PICARD_CUDA(cudaMemcpyAsync(dmean.p, mean_host.data(), sizeof(double) * nf, cudaMemcpyHostToDevice, st));
   }
+  mark("centering");
   if (!whiten) return;
   if (nc > nf)  // whitening.rs:51-58
     throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: n_components (" + std::to_string(nc) + ") cannot exceed n_features (" +
@@ -105,14 +116,17 @@ void center_whiten_device(const double* d_x, int nf, int64_t t_local, int64_t ld
   // W = I, bias = mean) + one allreduce + a single-CTA Jacobi eigensolver.
   const size_t nn = (size_t)nf * nf;
   DevBuf<double> eye(nn), mom((size_t)mom_size(nf) + MOM_EXTRA), partial(pass_workspace_doubles(nf, sm_count)), V(nn), ev((size_t)nf);
+  mark("whiten: allocations");
   stats->kernel_launches += small::set_identity(eye.p, nf, st);
   PassLaunch L;
   L.d_x = d_x; L.ldx = ldx; L.t_local = t_local; L.n_in = nf; L.n_out = nf; L.d_w = eye.p; L.ldw = nf;
   L.d_bias = centering ? dmean.p : nullptr; L.dens = DENS_LINEAR; L.alpha = 1.0; L.mode = PASS_GRAD; L.want_h = false;
   L.d_partial = partial.p; L.d_mom = mom.p; L.d_out = nullptr; L.ld_out = 0; L.sm_count = sm_count; L.stream = st;
   stats->kernel_launches += launch_pass(L);
+  mark("whiten: covariance pass");
   comm_allreduce_sum(comm, mom.p + mom_off_gr(nf), nn, st);
   stats->kernel_launches += small::jacobi_eigh(mom.p + mom_off_gr(nf), nf, V.p, ev.p, st);
+  mark("whiten: eigensolver");
   std::vector<double> evals((size_t)nf), U(nn);
   PICARD_CUDA(cudaMemcpyAsync(evals.data(), ev.p, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
   PICARD_CUDA(cudaMemcpyAsync(U.data(), V.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
@@ -136,70 +150,132 @@ void center_whiten_device(const double* d_x, int nf, int64_t t_local, int64_t ld
   }
 }
 
-// Device (rows x cols, leading dimension src_ld) -> pageable host (rows x cols, contiguous), pipelined: the GPU copies
-// chunk k into one of two pinned staging buffers while host threads move chunk k-1 into the destination (a fresh malloc:
-// the first touch of its pages is the slow part, so it is spread over several threads).  A plain cudaMemcpy2D into
-// pageable memory ran at ~2 GB/s on the B200 hosts; this runs at the speed of the page faults (~10 GB/s).
+// Device (rows x cols, leading dimension src_ld) -> pageable host (rows x cols, contiguous).  A plain cudaMemcpy2D into
+// pageable memory ran at ~2 GB/s on the B200 hosts.  Here W worker threads each run their own two-deep pipeline on their
+// own stream: DMA a chunk into a pinned staging buffer, then memcpy it into the destination while the next chunk is in
+// flight.  No cross-thread synchronisation; PCIe and host memory bandwidth are both kept busy.
+namespace {
+struct StagingArena {  // process-wide pinned staging, allocated once (page-locking is slow), reused by every call
+  std::mutex mu;
+  unsigned char* base = nullptr;
+  size_t bytes = 0;
+  bool busy = false;
+};
+StagingArena g_arena;
+constexpr size_t kStageBytes = (size_t)16 << 20;
+constexpr int kMaxWorkers = 8;
+}  // namespace
+
 static void d2h_pipelined(double* dst, const double* src_dev, int64_t src_ld, int64_t rows, int64_t cols, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return;
   const size_t row_bytes = sizeof(double) * (size_t)cols;
   const size_t total = row_bytes * (size_t)rows;
-  if (total < ((size_t)8 << 20)) {  // small: one plain copy
+  if (total < ((size_t)32 << 20)) {  // small: one plain copy
     PICARD_CUDA(cudaMemcpy2DAsync(dst, row_bytes, src_dev, sizeof(double) * src_ld, row_bytes, rows, cudaMemcpyDeviceToHost, st));
     PICARD_CUDA(cudaStreamSynchronize(st));
     return;
   }
-  const size_t chunk_target = (size_t)64 << 20;
-  // chunk = a block of whole rows, or a column range of one row when rows are longer than the staging buffer
-  const int64_t cols_per_chunk = row_bytes > chunk_target ? (int64_t)(chunk_target / sizeof(double)) : cols;
-  const int64_t rows_per_chunk = row_bytes > chunk_target ? 1 : std::max<int64_t>(1, (int64_t)(chunk_target / row_bytes));
-  const size_t chunk_bytes = sizeof(double) * (size_t)cols_per_chunk * (size_t)rows_per_chunk;
-  PinnedBuf<unsigned char> stage0(chunk_bytes), stage1(chunk_bytes);
-  unsigned char* stage[2] = {stage0.p, stage1.p};
-  cudaEvent_t ev[2];
-  PICARD_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  PICARD_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-  struct EvDel { cudaEvent_t* e; ~EvDel() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } edel{ev};
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nworkers = (int)std::max(1u, std::min((unsigned)kMaxWorkers, hw ? hw / 2 : 2u));
+  // staging: the shared arena if it is free, otherwise a private allocation (concurrent calls)
+  const size_t need = (size_t)nworkers * 2 * kStageBytes;
+  unsigned char* stage_base = nullptr;
+  bool from_arena = false;
+  {
+    std::lock_guard<std::mutex> lk(g_arena.mu);
+    if (!g_arena.busy) {
+      if (g_arena.bytes < need) {
+        if (g_arena.base) cudaFreeHost(g_arena.base);
+        g_arena.base = nullptr; g_arena.bytes = 0;
+        if (cudaMallocHost(&g_arena.base, need) == cudaSuccess) g_arena.bytes = need; else cudaGetLastError();
+      }
+      if (g_arena.base) { g_arena.busy = true; from_arena = true; stage_base = g_arena.base; }
+    }
+  }
+  PinnedBuf<unsigned char> private_stage(from_arena ? 1 : need);
+  if (!from_arena) stage_base = private_stage.p;
+  struct ArenaRelease { bool on; ~ArenaRelease() { if (on) { std::lock_guard<std::mutex> lk(g_arena.mu); g_arena.busy = false; } } } rel{from_arena};
+
+  // chunks: a block of whole rows, or a column range of one row when a row is longer than a staging buffer
+  const int64_t cols_per_chunk = row_bytes > kStageBytes ? (int64_t)(kStageBytes / sizeof(double)) : cols;
+  const int64_t rows_per_chunk = row_bytes > kStageBytes ? 1 : std::max<int64_t>(1, (int64_t)(kStageBytes / row_bytes));
   struct Chunk { int64_t r0, nr, c0, nc; };
   std::vector<Chunk> chunks;
   for (int64_t r = 0; r < rows; r += rows_per_chunk)
     for (int64_t c = 0; c < cols; c += cols_per_chunk)
       chunks.push_back({r, std::min(rows_per_chunk, rows - r), c, std::min(cols_per_chunk, cols - c)});
-  unsigned hw = std::thread::hardware_concurrency();
-  const int nthreads = (int)std::max(1u, std::min(16u, hw ? hw : 4u));
-  auto drain = [&](const Chunk& ch, const unsigned char* sbuf) {  // staging (nr x nc, dense) -> dst
-    const size_t cb = sizeof(double) * (size_t)ch.nc;
-    const size_t bytes = cb * (size_t)ch.nr;
-    std::vector<std::thread> th;
-    const size_t per = (bytes + nthreads - 1) / nthreads;
-    for (int t = 0; t < nthreads; ++t) {
+  cudaEvent_t ready;
+  PICARD_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  PICARD_CUDA(cudaEventRecord(ready, st));  // the source is complete once everything queued on `st` so far has run
+  int device = 0;
+  PICARD_CUDA(cudaGetDevice(&device));
+  std::vector<int> status((size_t)nworkers, 0);
+  std::vector<std::thread> th;
+  for (int w = 0; w < nworkers; ++w) {
+    th.emplace_back([&, w] {
+      if (cudaSetDevice(device) != cudaSuccess) { status[w] = 1; return; }
+      cudaStream_t s; cudaEvent_t ev[2];
+      if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { status[w] = 1; return; }
+      cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+      cudaStreamWaitEvent(s, ready, 0);
+      unsigned char* stg[2] = {stage_base + (size_t)(2 * w) * kStageBytes, stage_base + (size_t)(2 * w + 1) * kStageBytes};
+      std::vector<size_t> mine;
+      for (size_t k = (size_t)w; k < chunks.size(); k += (size_t)nworkers) mine.push_back(k);
+      auto drain = [&](const Chunk& ch, const unsigned char* sbuf) {
+        const size_t cb = sizeof(double) * (size_t)ch.nc;
+        for (int64_t r = 0; r < ch.nr; ++r)
+          memcpy(dst + (size_t)(ch.r0 + r) * (size_t)cols + (size_t)ch.c0, sbuf + (size_t)r * cb, cb);
+      };
+      for (size_t i = 0; i <= mine.size(); ++i) {
+        if (i < mine.size()) {
+          const Chunk& ch = chunks[mine[i]];
+          if (cudaMemcpy2DAsync(stg[i & 1], sizeof(double) * ch.nc, src_dev + (size_t)ch.r0 * src_ld + ch.c0, sizeof(double) * src_ld,
+                                sizeof(double) * ch.nc, ch.nr, cudaMemcpyDeviceToHost, s) != cudaSuccess) status[w] = 1;
+          cudaEventRecord(ev[i & 1], s);
+        }
+        if (i > 0) {
+          if (cudaEventSynchronize(ev[(i - 1) & 1]) != cudaSuccess) status[w] = 1;
+          drain(chunks[mine[i - 1]], stg[(i - 1) & 1]);
+        }
+      }
+      cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); cudaStreamDestroy(s);
+    });
+  }
+  for (auto& t : th) t.join();
+  cudaEventDestroy(ready);
+  for (int w = 0; w < nworkers; ++w)
+    if (status[w]) throw Error(PICARD_COMPUTATION_ERROR, std::string("Computation error: CUDA failure in the device-to-host copy: ") +
+                                                             cudaGetErrorString(cudaGetLastError()));
+}
+
+// Result buffers are released with free() (picard_result_free).
+static double* alloc_result(size_t count) {
+  void* p = malloc(sizeof(double) * (count ? count : 1));
+  if (!p) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: out of host memory");
+  return (double*)p;
+}
+
+// The `sources` result (nc x T doubles, 10 GB at c3) is a fresh allocation whose pages are first touched by the D2H
+// copy: ~2.6 M page faults that cap the copy at a few GB/s.  They are taken here instead, by background threads, while
+// the GPU runs the solver; join() before the copy.
+struct Prefault {
+  std::vector<std::thread> th;
+  void start(double* p, size_t count) {
+    const size_t bytes = sizeof(double) * count;
+    if (bytes < ((size_t)64 << 20)) return;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 2u));
+    unsigned char* base = reinterpret_cast<unsigned char*>(p);
+    const size_t per = ((bytes / n) + 4095) & ~(size_t)4095;
+    for (int t = 0; t < n; ++t) {
       const size_t a = (size_t)t * per, b = std::min(bytes, a + per);
       if (a >= b) break;
-      th.emplace_back([=] {
-        size_t off = a;
-        while (off < b) {  // copy [off, b) of the dense chunk, row by row of the destination
-          const size_t row = off / cb, in_row = off % cb;
-          const size_t n = std::min(b - off, cb - in_row);
-          memcpy(reinterpret_cast<unsigned char*>(dst + (size_t)(ch.r0 + (int64_t)row) * (size_t)cols + (size_t)ch.c0) + in_row, sbuf + off, n);
-          off += n;
-        }
-      });
-    }
-    for (auto& t : th) t.join();
-  };
-  for (size_t k = 0; k <= chunks.size(); ++k) {
-    if (k < chunks.size()) {
-      const Chunk& ch = chunks[k];
-      PICARD_CUDA(cudaMemcpy2DAsync(stage[k & 1], sizeof(double) * ch.nc, src_dev + (size_t)ch.r0 * src_ld + ch.c0, sizeof(double) * src_ld,
-                                    sizeof(double) * ch.nc, ch.nr, cudaMemcpyDeviceToHost, st));
-      PICARD_CUDA(cudaEventRecord(ev[k & 1], st));
-    }
-    if (k > 0) {
-      PICARD_CUDA(cudaEventSynchronize(ev[(k - 1) & 1]));
-      drain(chunks[k - 1], stage[(k - 1) & 1]);
+      th.emplace_back([=] { for (size_t o = a; o < b; o += 4096) base[o] = 0; });
     }
   }
-}
+  void join() { for (auto& t : th) if (t.joinable()) t.join(); th.clear(); }
+  ~Prefault() { join(); }
+};
 
 static double* dup_host(const double* p, size_t n) {
   double* o = (double*)malloc(sizeof(double) * (n ? n : 1));
@@ -208,9 +284,25 @@ static double* dup_host(const double* p, size_t n) {
   return o;
 }
 
+namespace {
+// PICARD_TRACE=1: wall-clock stage timings of the fit pipeline on stderr (diagnostics only)
+struct Trace {
+  bool on = getenv("PICARD_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what, cudaStream_t st) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[picard trace] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_t ldx, const picard_config_t& cfg,
                 double* d_sources, int64_t lds, picard_result_t* out) {
   memset(out, 0, sizeof *out);
+  Trace trace;
   config_validate(cfg);                                                       // solver.rs:46
   if (n_features <= 0 || n_samples <= 0)                                      // solver.rs:50-54
     throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
@@ -248,6 +340,7 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   std::vector<double> mean, K;
   center_whiten_device(d_x, nf, t_local, ldx, (int)ncomp, cfg.centering != 0, cfg.whiten != 0, cfg.comm, guard.sm_count, st, mean, K,
                        t_total, &stats);                                      // solver.rs:77-93
+  trace.mark("center + whiten", st);
   const int nc = cfg.whiten ? (int)ncomp : nf;                                // solver.rs:95 (quirk Q13)
   pass_padded_size(nc);
 
@@ -276,8 +369,10 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   }
 
   // x1 = K (x - mean) when a warm start needs the whitened data itself (solver.rs:124-137)
+  trace.mark("w_init", st);
   const int64_t ld1 = round_up(t_local, 16);
   DevBuf<double> x1((size_t)nc * ld1);
+  trace.mark("alloc x1", st);
   std::vector<double> eye_nc;
   if (cfg.jade_it >= 0) {
     if (cfg.verbose && (!cfg.comm || comm_rank(cfg.comm) == 0)) printf("Running %lld iterations of JADE...\n", (long long)cfg.jade_it);
@@ -297,15 +392,25 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   else a_total = w_init;
   stats.kernel_launches += apply_device(a_total.data(), mean.empty() ? nullptr : mean.data(), nc, nf, d_x, ldx, x1.p, ld1, t_local,
                                         guard.sm_count, st);
+  trace.mark("x1 = w_init K (x - mean)", st);
   PICARD_CUDA(cudaEventRecord(e1, st));
   PICARD_CUDA(cudaStreamSynchronize(st));
   float pre_ms = 0.f;
   PICARD_CUDA(cudaEventElapsedTime(&pre_ms, e0, e1));
   stats.preprocess_ms = pre_ms;
 
+  const bool keep_dev = (cfg.flags & PICARD_FLAG_KEEP_SOURCES_ON_DEVICE) != 0;
+  struct HostBuf { double* p = nullptr; ~HostBuf() { free(p); } double* release() { double* q = p; p = nullptr; return q; } } src_guard;
+  Prefault prefault;
+  if (!keep_dev) {
+    src_guard.p = alloc_result((size_t)nc * t_local);
+    prefault.start(src_guard.p, (size_t)nc * t_local);
+  }
   if (cfg.verbose && (!cfg.comm || comm_rank(cfg.comm) == 0)) printf("Running Picard...\n");
   CoreSolver core(x1.p, nc, t_local, ld1, cfg, extended && cfg.whiten, guard.sm_count, st);  // solver.rs:143-166
+  trace.mark("core solver setup", st);
   core.run(cfg.max_iter);
+  trace.mark("core loop", st);
   std::vector<double> wc((size_t)nc * nc), signs((size_t)nc);
   core.state(wc.data(), signs.data(), nullptr, nullptr, nullptr, nullptr);
   std::vector<double> wfull((size_t)nc * nc);
@@ -320,25 +425,23 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   stats.kernel_launches += cs.kernel_launches;
   stats.pass_ms_fused = cs.pass_ms_fused; stats.pass_ms_grad = cs.pass_ms_grad; stats.pass_ms_loss = cs.pass_ms_loss;
   stats.grady_passes = cs.grady_passes; stats.pass_ms_grady = cs.pass_ms_grady;
-  const bool keep_dev = (cfg.flags & PICARD_FLAG_KEEP_SOURCES_ON_DEVICE) != 0;
   double* host_sources = nullptr;
+  prefault.join();
   if (d_sources) {
     stats.kernel_launches += apply_device(wc.data(), nullptr, nc, nc, x1.p, ld1, d_sources, lds, t_local, guard.sm_count, st);
     if (!keep_dev) {
-      host_sources = (double*)malloc(sizeof(double) * (size_t)nc * t_local);
-      if (!host_sources) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: out of host memory");
-      d2h_pipelined(host_sources, d_sources, lds, nc, t_local, st);
+      d2h_pipelined(src_guard.p, d_sources, lds, nc, t_local, st);
+      host_sources = src_guard.release(); out->sources = host_sources;
       stats.d2h_bytes += (int64_t)sizeof(double) * nc * t_local;
     }
   } else if (!keep_dev) {
     DevBuf<double> ysrc((size_t)nc * ld1);
     stats.kernel_launches += apply_device(wc.data(), nullptr, nc, nc, x1.p, ld1, ysrc.p, ld1, t_local, guard.sm_count, st);
-    host_sources = (double*)malloc(sizeof(double) * (size_t)nc * t_local);
-    if (!host_sources) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: out of host memory");
     cudaEvent_t d0, d1;
     PICARD_CUDA(cudaEventCreate(&d0)); PICARD_CUDA(cudaEventCreate(&d1));
     PICARD_CUDA(cudaEventRecord(d0, st));
-    d2h_pipelined(host_sources, ysrc.p, ld1, nc, t_local, st);
+    d2h_pipelined(src_guard.p, ysrc.p, ld1, nc, t_local, st);
+    host_sources = src_guard.release(); out->sources = host_sources;
     PICARD_CUDA(cudaEventRecord(d1, st));
     PICARD_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f; cudaEventElapsedTime(&ms, d0, d1); stats.d2h_ms += ms;
@@ -346,6 +449,7 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
     stats.d2h_bytes += (int64_t)sizeof(double) * nc * t_local;
   }
 
+  trace.mark("sources + D2H", st);
   out->n_components = nc; out->n_features = nf; out->n_samples = t_local;
   out->whitening = cfg.whiten ? dup_host(K.data(), K.size()) : nullptr;
   out->unmixing = dup_host(wfull.data(), wfull.size());

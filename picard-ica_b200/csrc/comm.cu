@@ -56,7 +56,7 @@ void nccl_check(int rc, const char* what) {
                                               (a.get_error_string ? a.get_error_string(rc) : "unknown"));
   }
 }
-constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclInt64 = 4, kNcclMax = 2;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
 }  // namespace
 
 void comm_unique_id(char id[PICARD_UNIQUE_ID_BYTES]) {

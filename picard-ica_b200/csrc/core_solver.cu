@@ -146,12 +146,12 @@ void CoreSolver::fetch_scalars() {
 void CoreSolver::try_point(double alpha, bool speculate) {
   const int n = dims_.n;
   stats_.ls_tries++;
-  if (dims_.ortho) {
-    stats_.kernel_launches += small::matrix_exp(D_, alpha, sc_host_.p->norm_d, n, ew_, M_, st_);  // core.rs:119
+  if (dims_.ortho) {  // W' = expm(alpha D) W in one cooperative kernel (core.rs:119,125)
+    stats_.kernel_launches += small::matrix_exp(D_, alpha, sc_host_.p->norm_d, n, ew_, nullptr, st_, W_, Wt_);
   } else {
     stats_.kernel_launches += small::eye_plus_scaled(D_, alpha, M_, n, st_);                      // core.rs:121
+    stats_.kernel_launches += small::matmul(M_, W_, Wt_, n, false, 1.0, false, st_);              // core.rs:125
   }
-  stats_.kernel_launches += small::matmul(M_, W_, Wt_, n, false, 1.0, false, st_);                // core.rs:125
   if (!dims_.ortho)  // -log|det W'| term of the loss (core.rs:51-70)
     stats_.kernel_launches += small::sln_det(Wt_, n, lu_work_, mom_trial_ + mom_size(n), st_);
   pass(Wt_, speculate ? PASS_FUSED : PASS_LOSS, mom_trial_);                                      // core.rs:124,127

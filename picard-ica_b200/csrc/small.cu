@@ -3,7 +3,11 @@
 
 #include <cmath>
 
+#include <cooperative_groups.h>
+
 #include "pass.cuh"  // moment-buffer layout helpers
+
+namespace cg = cooperative_groups;
 
 namespace picard {
 namespace small {
@@ -270,10 +274,34 @@ __global__ void __launch_bounds__(BT1) front_kernel(FrontArgs a) {
   if (tid == 0) a.sc->norm_d = nd;
 }
 
+// one warp: lane-strided partial sums + shuffle tree (fixed order, deterministic)
+__device__ double loss_of_point_warp(const CoreDims& d, const double* mom, const double* signs, bool* singular) {
+  const int n = d.n, lane = threadIdx.x & 31;
+  const double tf = d.t_total;
+  *singular = false;
+  double base = 0.0;
+  if (!d.ortho) {
+    const double* ex = mom + mom_size(n);
+    if (ex[1] == 0.0) { *singular = true; return 1e15; }
+    base = -ex[0];
+  }
+  const double* L = mom + mom_off_ll(n);
+  const double* Sq = mom + mom_off_sq(n);
+  double part = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    const double s = signs ? signs[i] : 1.0;
+    part += s * L[i] / tf;
+    if (d.extended && !d.ortho) part += 0.5 * Sq[i] / tf;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  return base + part;
+}
+
 __global__ void loss_kernel(CoreDims d, const double* mom, const double* signs, CoreScalars* sc, int which) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   bool sing;
-  const double l = loss_of_point(d, mom, signs, &sing);
+  const double l = loss_of_point_warp(d, mom, signs, &sing);
+  if (threadIdx.x != 0) return;
   if (which == 0) {
     sc->new_loss = l;
     sc->accept = (l < sc->current_loss) ? 1 : 0;
@@ -356,44 +384,88 @@ __global__ void __launch_bounds__(256) matmul_kernel(const double* A, const doub
     }
 }
 
-// one Taylor term of matrix_exp (math.rs:58-66): term_k = term_{k-1} A / k ; result += term_k ;
-// slots[k] = max |term_k| ; skipped entirely once a previous term fell below 1e-16 (the `break`).
-__global__ void __launch_bounds__(256) expm_term_kernel(const double* term_prev, const double* As, double* term_new, double* result,
-                                                        double* slots, int n, int k) {
-  if (slots[k - 1] < 1e-16) return;  // uniform across the grid: slots[k-1] was finalised by the previous launch
-  double acc[2][2];
-  tile_mm<false>(term_prev, n, As, n, n, n, n, blockIdx.y, blockIdx.x, acc);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double mx = 0.0;
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int i = blockIdx.y * 32 + ty + 16 * a, j = blockIdx.x * 32 + tx + 16 * b;
-      if (i < n && j < n) {
-        const double v = acc[a][b] / (double)k;
-        term_new[(size_t)i * n + j] = v;
-        result[(size_t)i * n + j] += v;
-        mx = fmax(mx, fabs(v));
-      }
-    }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(&slots[k]), (unsigned long long)__double_as_longlong(mx));
-}
-// A_s = D * alpha / scale ; term_1 = A_s ; result = I + A_s ; slots[0] = 1, slots[1] = max|A_s|, others 0
-__global__ void expm_prepare_kernel(const double* D, double alpha, double scale, int n, double* As, double* term, double* result,
-                                    double* slots) {
+// ---------------------------------------------------------------------------------------------------
+// matrix_exp (math.rs:38-74) as ONE cooperative kernel: scaling, Taylor terms with the reference's early exit
+// (max |term_k| < 1e-16, <= 30 terms), s squarings, and optionally the product with W (core.rs:125) -- grid.sync()
+// between dependent steps instead of ~35 kernel launches per line-search try.  Work unit = 32 x 32 output tile.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) expm_coop_kernel(const double* __restrict__ D, double alpha, double scale, double first_norm, int s,
+                                                        int n, double* As, double* T0, double* T1, double* R0, double* R1, double* slots,
+                                                        double* out, const double* W, double* Wt) {
+  cg::grid_group grid = cg::this_grid();
   __shared__ double sh[33];
-  double mx = 0.0;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+  const int nt = (n + 31) / 32, ntiles = nt * nt;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // phase 0: A_s = D alpha / scale ; term_1 = A_s ; result = I + A_s
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
     const double v = (D[e] * alpha) / scale;
-    As[e] = v; term[e] = v;
-    result[e] = ((e / n == e % n) ? 1.0 : 0.0) + v;
-    mx = fmax(mx, fabs(v));
+    As[e] = v; T1[e] = v;
+    R0[e] = ((e / n == e % n) ? 1.0 : 0.0) + v;
   }
-  mx = block_max(mx, sh);
-  if (threadIdx.x < 32) slots[threadIdx.x] = threadIdx.x == 0 ? 1.0 : (threadIdx.x == 1 ? mx : 0.0);
+  if (blockIdx.x == 0 && threadIdx.x < 32) slots[threadIdx.x] = 0.0;
+  grid.sync();
+  double* tp = T1; double* tn = T0;
+  double prev = first_norm;  // max |term_1| = max |D alpha| / scale (exact: scale is a power of two)
+  for (int k = 2; k <= 30; ++k) {
+    if (prev < 1e-16) break;  // the `break` of math.rs:63-65 (uniform: every thread reads the same value)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int bi = tile / nt, bj = tile % nt;
+      double acc[2][2];
+      tile_mm<false>(tp, n, As, n, n, n, n, bi, bj, acc);
+      double mx = 0.0;
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int i = bi * 32 + ty + 16 * a, j = bj * 32 + tx + 16 * b;
+          if (i < n && j < n) {
+            const double v = acc[a][b] / (double)k;
+            tn[(size_t)i * n + j] = v;
+            R0[(size_t)i * n + j] += v;
+            mx = fmax(mx, fabs(v));
+          }
+        }
+      mx = block_max(mx, sh);
+      if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(&slots[k]), (unsigned long long)__double_as_longlong(mx));
+    }
+    grid.sync();
+    prev = *reinterpret_cast<volatile double*>(&slots[k]);
+    double* t = tp; tp = tn; tn = t;
+  }
+  // squaring (math.rs:69-71)
+  double* cur = R0; double* nxt = R1;
+  for (int q = 0; q < s; ++q) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int bi = tile / nt, bj = tile % nt;
+      double acc[2][2];
+      tile_mm<false>(cur, n, cur, n, n, n, n, bi, bj, acc);
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int i = bi * 32 + ty + 16 * a, j = bj * 32 + tx + 16 * b;
+          if (i < n && j < n) nxt[(size_t)i * n + j] = acc[a][b];
+        }
+    }
+    grid.sync();
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  if (out != nullptr)
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) out[e] = cur[e];
+  if (W != nullptr && Wt != nullptr) {  // W' = expm(alpha D) W   (core.rs:125)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int bi = tile / nt, bj = tile % nt;
+      double acc[2][2];
+      tile_mm<false>(cur, n, W, n, n, n, n, bi, bj, acc);
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int i = bi * 32 + ty + 16 * a, j = bj * 32 + tx + 16 * b;
+          if (i < n && j < n) Wt[(size_t)i * n + j] = acc[a][b];
+        }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -788,35 +860,26 @@ int clear_memory(CoreScalars* sc, cudaStream_t st) {
   return 1;
 }
 
-int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWork& w, double* out, cudaStream_t st) {
+int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWork& w, double* out, cudaStream_t st, const double* W,
+               double* Wt) {
   const double norm = norm_d * alpha;  // max |D * alpha| (alpha > 0)
-  int launches = 0;
   if (!(norm >= 1e-15)) {  // math.rs:43-45 (NaN norms cannot occur: fmax ignores NaN entries)
-    return set_identity(out, n, st);
+    int launches = 0;
+    if (out) launches += set_identity(out, n, st);
+    if (W && Wt) { PICARD_CUDA(cudaMemcpyAsync(Wt, W, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, st)); }
+    return launches;
   }
-  const int s = (int)std::fmax(std::ceil(std::log2(norm)), 0.0);
-  const double scale = std::ldexp(1.0, s);
-  int threads = n * n >= 1024 ? 1024 : ((n * n + 31) / 32) * 32;
-  double* res = (s == 0) ? out : w.res0;
-  expm_prepare_kernel<<<1, threads, 0, st>>>(D, alpha, scale, n, w.As, w.term1, res, w.slots);
-  LAUNCH_CHECK();
-  ++launches;
-  dim3 grid((n + 31) / 32, (n + 31) / 32);
-  for (int k = 2; k <= 30; ++k) {
-    const double* tp = (k & 1) ? w.term0 : w.term1;  // term_{k-1}: term_1 lives in term1
-    double* tn = (k & 1) ? w.term1 : w.term0;
-    expm_term_kernel<<<grid, 256, 0, st>>>(tp, w.As, tn, res, w.slots, n, k);
-    LAUNCH_CHECK();
-    ++launches;
-  }
-  // squaring (math.rs:69-71)
-  double* cur = res;
-  for (int i = 0; i < s; ++i) {
-    double* nxt = (i == s - 1) ? out : (cur == w.res0 ? w.res1 : w.res0);
-    launches += matmul(cur, cur, nxt, n, false, 1.0, false, st);
-    cur = nxt;
-  }
-  return launches;
+  int s = (int)std::fmax(std::ceil(std::log2(norm)), 0.0);
+  double scale = std::ldexp(1.0, s);
+  double first_norm = norm / scale;
+  const int nt = (n + 31) / 32;
+  int grid = nt * nt;
+  if (grid > 64) grid = 64;
+  double* res0 = w.res0; double* res1 = w.res1; double* As = w.As; double* t0 = w.term0; double* t1 = w.term1; double* slots = w.slots;
+  void* args[] = {(void*)&D, (void*)&alpha, (void*)&scale, (void*)&first_norm, (void*)&s, (void*)&n, (void*)&As, (void*)&t0, (void*)&t1,
+                  (void*)&res0, (void*)&res1, (void*)&slots, (void*)&out, (void*)&W, (void*)&Wt};
+  PICARD_CUDA(cudaLaunchCooperativeKernel((const void*)expm_coop_kernel, dim3(grid), dim3(256), args, 0, st));
+  return 1;
 }
 
 int sln_det(const double* A, int n, double* work, double* out2, cudaStream_t st) {

@@ -74,7 +74,9 @@ int clear_memory(CoreScalars* sc, cudaStream_t st);
 
 // ---- matrix_exp (math.rs:38-74): out = expm(alpha * D). norm_d = max|D| known to the host.
 struct ExpmWork { double* As; double* term0; double* term1; double* res0; double* res1; double* slots; };
-int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWork& w, double* out, cudaStream_t st);
+// One cooperative kernel.  out (may be NULL) = expm(alpha D); if W and Wt are given, Wt = expm(alpha D) W (core.rs:125).
+int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWork& w, double* out, cudaStream_t st,
+               const double* W = nullptr, double* Wt = nullptr);
 
 // ---- signed log-determinant by LU with partial pivoting (math.rs:84-88): out2 = [logabs, sign]
 int sln_det(const double* A, int n, double* work, double* out2, cudaStream_t st);

@@ -113,7 +113,7 @@ def cpu_oracle_rate(wl, t_cpu, max_iter, threads=None):
                 cores=orc.get_threads(), loss_evals=r.loss_evals)
 
 
-def run_reference(args, wl, rank):
+def run_reference(args, wl, rank, out):
     if rank != 0:
         return
     ncores = os.cpu_count() or 1
@@ -132,15 +132,28 @@ def run_reference(args, wl, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(len(per_step), 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload},
+        "config": {"workload": wl["desc"], "name": args.workload, "n": wl["n"], "t_total": wl["t"], "t_per_gpu": wl["t"],
+                   "parallelism": "host CPU, all cores (OpenBLAS threads); reference arm runs on rank 0 only",
+                   "l2": "n/a (CPU)", "timing": "wall clock of the oracle core loop on the bounded sample, scaled linearly in T"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything libraries print there (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    try:
+        _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -159,7 +172,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, wl, rank)
+        run_reference(args, wl, rank, out)
         return
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
@@ -332,7 +345,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "passes": pass_mix,
             "state": {"n_iterations": state["n_iterations"], "gradient_norm": state["gradient_norm"], "loss": state["loss"]},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if comm is not None:
         comm.close()
     if world > 1:

@@ -195,6 +195,10 @@ int picard_center_whiten_device(const double* d_x, int64_t n_features, int64_t n
 int picard_jade(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, int64_t max_iter, double tol,
                 int32_t verbose, int32_t device, double* w, int64_t* sweeps, char* err, size_t errlen);
 
+/* jade.rs:78-131 alone (test hook): cumulant matrices Q_ij, i <= j, as out[m][k][l] with m enumerating (i, j) row-major. */
+int picard_jade_cumulants(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, int32_t device, double* out, char* err,
+                          size_t errlen);
+
 /* ---- synthetic data: counter-based, identical for any shard layout ------------------ */
 /* Writes sources S[i, t_offset + s] for s in [0, n_samples) into d_out (n x n_samples, leading dim ld):
  * row i < n_laplace: Laplace(b = 1/sqrt 2) (unit variance); else uniform on [-sqrt 3, sqrt 3]. */

@@ -16,7 +16,7 @@ EXPORTED = [
     "picard_fit", "picard_fit_device", "picard_transform", "picard_result_free", "picard_core_create", "picard_core_run",
     "picard_core_reset", "picard_core_state", "picard_core_stats", "picard_core_destroy", "picard_eval_moments", "picard_eval_moments_device",
     "picard_eval_point", "picard_matrix_exp", "picard_sln_det", "picard_sym_decorrelation", "picard_compute_direction",
-    "picard_center_whiten", "picard_center_whiten_device", "picard_jade", "picard_synth_sources", "picard_apply_device", "picard_comm_unique_id",
+    "picard_center_whiten", "picard_center_whiten_device", "picard_jade", "picard_jade_cumulants", "picard_synth_sources", "picard_apply_device", "picard_comm_unique_id",
     "picard_comm_create", "picard_comm_rank", "picard_comm_size", "picard_comm_destroy",
 ]
 

@@ -396,6 +396,20 @@ int picard_jade(const double* x, int64_t n, int64_t n_samples, int64_t row_strid
   });
 }
 
+int picard_jade_cumulants(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, int32_t device, double* out, char* err,
+                          size_t errlen) {
+  return guarded(err, errlen, [&] {
+    DeviceGuard guard(device);
+    cudaStream_t st;
+    PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
+    Staged xs(x, n, n_samples, row_stride, st);
+    picard_stats_t stats;
+    memset(&stats, 0, sizeof stats);
+    jade_cumulants_device(xs.buf.p, (int)n, n_samples, xs.ld, (double)n_samples, nullptr, guard.sm_count, st, out, &stats);
+  });
+}
+
 int picard_synth_sources(double* d_out, int64_t n, int64_t n_samples, int64_t ld, int64_t t_offset, int64_t n_laplace, uint64_t seed,
                          int32_t device, void* stream) {
   return guarded(nullptr, 0, [&] {

@@ -39,7 +39,7 @@ static EncodeTiledFn get_encode() {
 
 // X is (n_in x t_local) f64, row-major, leading dimension ldx. Box = 16 samples x NP rows, SWIZZLE_128B;
 // rows >= n_in and samples >= t_local are zero-filled by the TMA unit.
-static CUtensorMap make_tmap(const double* d_x, int64_t ldx, int64_t t_local, int n_in, int np) {
+CUtensorMap make_tmap(const double* d_x, int64_t ldx, int64_t t_local, int n_in, int np) {
   if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0 || (ldx & 1) != 0)
     throw Error(PICARD_INVALID_DIMENSIONS,
                 "Invalid dimensions: device sample matrix must be 16-byte aligned with an even row stride (TMA)");

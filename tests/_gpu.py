@@ -99,3 +99,13 @@ def jade(x, max_iter, tol=1e-6, device=0):
     st = _ffi.lib().picard_jade(_p(x), C.c_int64(n), C.c_int64(t), C.c_int64(x.strides[0] // 8), C.c_int64(max_iter), C.c_double(tol),
                                 C.c_int32(0), C.c_int32(device), _p(w), C.byref(sw), err, C.c_size_t(1024))
     return st, err.value.decode(), w, sw.value
+
+
+def jade_cumulants(x, device=0):
+    x = _c(x); n, t = x.shape
+    out = np.empty((n * (n + 1) // 2, n, n))
+    err = C.create_string_buffer(1024)
+    st = _ffi.lib().picard_jade_cumulants(_p(x), C.c_int64(n), C.c_int64(t), C.c_int64(x.strides[0] // 8), C.c_int32(device), _p(out), err,
+                                          C.c_size_t(1024))
+    _check(st, err)
+    return out

@@ -258,6 +258,41 @@ int64_t CoreSolver::run(int64_t max_new) {
   return done;
 }
 
+// ica_par (solver.rs:218-249): W <- symdecor(w_init); repeat: C = E[g(WX)X^T] - diag(E[g'(WX)]) W ; W <- symdecor(C).
+// E[g(WX) X^T] is the Gr moment of the ordinary gradient pass times W (W is orthogonal after symdecor, so
+// X^T = Y^T W^-T = Y^T W): no extra kernel for the N x T part.
+void CoreSolver::fastica(int64_t iters, double* w_host) {
+  const int n = dims_.n;
+  const size_t nn = (size_t)n * n;
+  DevBuf<double> work(4 * nn + n), tmp(nn);
+  DevBuf<int> d_status(1);
+  auto decorrelate = [&](const double* src, double* dst) {
+    stats_.kernel_launches += small::sym_decorrelation(src, n, work.p, dst, d_status.p, st_);
+    int status = 0;
+    PICARD_CUDA(cudaMemcpyAsync(&status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st_));
+    PICARD_CUDA(cudaStreamSynchronize(st_));
+    if (status != PICARD_OK) throw Error(PICARD_SINGULAR_MATRIX, "Singular matrix encountered during computation");  // math.rs:21-24
+  };
+  PICARD_CUDA(cudaMemcpyAsync(Wt_, w_host, sizeof(double) * nn, cudaMemcpyHostToDevice, st_));
+  decorrelate(Wt_, W_);
+  const bool from_x = pass_padded_size(n) <= 128;
+  for (int64_t it = 0; it < iters; ++it) {
+    if (from_x) {
+      eval_pass(W_, PASS_GRAD, false, dens_, alpha_, mom_cur_);
+      stats_.grad_passes++;
+    } else {  // N > 128: Y = W X kept by a LOSS pass, moments from the stored Y
+      if (!ybuf_.p) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: no memory for the Y store (needed for N > 128)");
+      eval_pass(W_, PASS_LOSS, false, dens_, alpha_, mom_cur_, true);
+      eval_pass(W_, PASS_GRADY, false, dens_, alpha_, mom_cur_);
+      stats_.loss_passes++; stats_.grady_passes++;
+    }
+    stats_.kernel_launches += small::fastica_matrix(mom_cur_, n, dims_.t_total, W_, tmp.p, Wt_, st_);
+    decorrelate(Wt_, W_);
+  }
+  PICARD_CUDA(cudaMemcpyAsync(w_host, W_, sizeof(double) * nn, cudaMemcpyDeviceToHost, st_));
+  PICARD_CUDA(cudaStreamSynchronize(st_));
+}
+
 void CoreSolver::hook_moments(const double* w_host, int mode, bool want_h, double* gr, double* sd, double* hr, double* sq,
                               double* lrow) {
   const int n = dims_.n;

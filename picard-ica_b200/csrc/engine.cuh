@@ -78,6 +78,8 @@ class CoreSolver {
   // Runs up to max_new further outer iterations. Returns the number performed in this call.
   int64_t run(int64_t max_new);
   void state(double* w, double* signs, int64_t* n_iterations, int32_t* converged, double* gradient_norm, double* loss);
+  // FastICA parallel iterations (ica_par, solver.rs:218-249) on this solver's data: w (n x n, host) in / out
+  void fastica(int64_t iters, double* w_host);
   const double* d_w() const { return W_; }
   const picard_stats_t& stats() const { return stats_; }
   bool converged() const { return converged_; }

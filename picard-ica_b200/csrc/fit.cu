@@ -306,8 +306,6 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   config_validate(cfg);                                                       // solver.rs:46
   if (n_features <= 0 || n_samples <= 0)                                      // solver.rs:50-54
     throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
-  if (cfg.fastica_it >= 0)
-    throw Error(PICARD_COMPUTATION_ERROR, "Computation error: the FastICA warm start (fastica_it) is not implemented on the device yet");
   DeviceGuard guard(cfg.device);
   cudaStream_t st;
   PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -374,16 +372,28 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   DevBuf<double> x1((size_t)nc * ld1);
   trace.mark("alloc x1", st);
   std::vector<double> eye_nc;
-  if (cfg.jade_it >= 0) {
-    if (cfg.verbose && (!cfg.comm || comm_rank(cfg.comm) == 0)) printf("Running %lld iterations of JADE...\n", (long long)cfg.jade_it);
+  if (cfg.jade_it >= 0 || cfg.fastica_it >= 0) {
+    const bool is_jade = cfg.jade_it >= 0;  // JADE takes priority (solver.rs:124-137; validate() forbids both)
+    if (cfg.verbose && (!cfg.comm || comm_rank(cfg.comm) == 0))
+      printf("Running %lld iterations of %s...\n", (long long)(is_jade ? cfg.jade_it : cfg.fastica_it), is_jade ? "JADE" : "FastICA");
     std::vector<double> a0;
     const double* a_ptr;
     if (cfg.whiten) a_ptr = K.data();
     else { a0.assign((size_t)nc * nc, 0.0); for (int i = 0; i < nc; ++i) a0[(size_t)i * nc + i] = 1.0; a_ptr = a0.data(); }
     stats.kernel_launches += apply_device(a_ptr, mean.empty() ? nullptr : mean.data(), nc, nf, d_x, ldx, x1.p, ld1, t_local,
                                           guard.sm_count, st);
-    jade_device(x1.p, nc, t_local, ld1, t_total, cfg.jade_it, 1e-6, cfg.verbose != 0, cfg.comm, guard.sm_count, st, w_init.data(),
-                nullptr, &stats);                                             // replaces w_init (quirk Q14)
+    if (is_jade) {
+      jade_device(x1.p, nc, t_local, ld1, t_total, cfg.jade_it, 1e-6, cfg.verbose != 0, cfg.comm, guard.sm_count, st, w_init.data(),
+                  nullptr, &stats);                                           // replaces w_init (quirk Q14)
+    } else {  // ica_par(&x1, &density, fastica_it, &w_init) -- starts from w_init (solver.rs:136)
+      picard_config_t fc = cfg;
+      fc.ortho = 1;  // gradient moments only (no H)
+      if (pass_padded_size(nc) <= 128) fc.flags |= PICARD_FLAG_NO_Y_STORE;  // the from-X gradient pass is used: no Y buffer needed
+      CoreSolver fica(x1.p, nc, t_local, ld1, fc, false, guard.sm_count, st);
+      fica.fastica(cfg.fastica_it, w_init.data());
+      stats.kernel_launches += fica.stats().kernel_launches;
+      if (cfg.verbose && (!cfg.comm || comm_rank(cfg.comm) == 0)) printf("FastICA pre-iterations complete.\n");
+    }
   }
 
   // x1 = w_init * K * (x - mean)  (solver.rs:140 with whitening.rs:110 folded in)

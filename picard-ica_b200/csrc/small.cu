@@ -910,6 +910,25 @@ int jacobi_eigh(double* A, int n, double* V, double* evals, cudaStream_t st) {
   return 1;
 }
 
+namespace {
+__global__ void fastica_a_kernel(const double* __restrict__ mom, int n, double t_total, double* __restrict__ A) {
+  const double* Gr = mom + mom_off_gr(n);
+  const double* Sd = mom + mom_off_sd(n);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+    const int i = e / n, j = e % n;
+    double v = Gr[e] / t_total;
+    if (i == j) v -= Sd[i] / t_total;
+    A[e] = v;
+  }
+}
+}  // namespace
+
+int fastica_matrix(const double* mom, int n, double t_total, const double* W, double* tmp, double* C, cudaStream_t st) {
+  fastica_a_kernel<<<ew_blocks((int64_t)n * n), 256, 0, st>>>(mom, n, t_total, tmp);
+  LAUNCH_CHECK();
+  return 1 + matmul(tmp, W, C, n, false, 1.0, false, st);
+}
+
 int sym_decorrelation(const double* W, int n, double* work, double* out, int* status_dev, cudaStream_t st) {
   double* wwt = work;
   double* U = work + (size_t)n * n;

@@ -81,6 +81,11 @@ int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWo
 // ---- signed log-determinant by LU with partial pivoting (math.rs:84-88): out2 = [logabs, sign]
 int sln_det(const double* A, int n, double* work, double* out2, cudaStream_t st);
 
+// FastICA fixed-point matrix (solver.rs:229-238) from the pass moments at Y = W X with W orthogonal:
+//   C = E[g(WX) X^T] - diag(E[g'(WX)]) W = (Gr / T - diag(Sd / T)) W     (X^T = Y^T W^-T = Y^T W)
+// tmp, C: n x n.
+int fastica_matrix(const double* mom, int n, double t_total, const double* W, double* tmp, double* C, cudaStream_t st);
+
 // ---- symmetric eigendecomposition, cyclic Jacobi, single CTA (K7): A (n x n, destroyed), eigenvalues
 // ascending in evals, eigenvectors in the COLUMNS of V.
 int jacobi_eigh(double* A, int n, double* V, double* evals, cudaStream_t st);

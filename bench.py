@@ -281,7 +281,12 @@ def _main(out):
         avg_ms = ms / cnt
         ach = flops / (avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": {"loss": "rb_loss_kernel (LOSS + Y store)", "grady": "rb_grady_kernel (stored-Y gradient)"}.get(name, f"pass_kernel<{name}>"), "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": ach / FP64_PEAK_TFLOPS, "traffic": None, "avg_launch_ms": avg_ms, "launches": cnt,
+                "frac": ach / FP64_PEAK_TFLOPS,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture at c3 on one GPU
+                # (profiles/summary_r01c.txt), scaled to this rank's share of the samples; null for kernels not captured
+                "traffic": {"loss": 20.437e9, "grady": 10.246e9}.get(name, None) and {"loss": 20.437e9, "grady": 10.246e9}[name] * (t_local / 1e7) * (n / 128.0)
+                if (n == 128) else None,
+                "algorithmic_bytes": (16.0 if name == "loss" else 8.0) * n * t_local, "avg_launch_ms": avg_ms, "launches": cnt,
                 "flops_per_launch": flops, "peak_source": "FP64 DMMA m8n8k4 microbenchmark measured by us "
                 "(profiles/microbench/fp64_pipes_r01.jsonl); MEASURED_PEAKS.json has no FP64 entry",
                 "share_of_step": ms / dev_ms, "hbm_gbs": 8.0 * n * t_local / (avg_ms * 1e-3) / 1e9}
@@ -302,6 +307,7 @@ def _main(out):
         torch.cuda.empty_cache()
         xh = x_host.numpy()
         cfg2 = P.PicardConfig(density=cfg.density, ortho=wl["ortho"], extended=wl["extended"], w_init=w0, comm=comm, device=local_rank)
+        os.environ.setdefault("PICARD_TRACE", "1")  # stage timings of every e2e call on stderr (a few extra stream syncs)
         runs = []
         for _rep in range(3):  # three complete calls; the median is reported, all three are listed
             res = None

@@ -108,6 +108,9 @@ int picard_abi_version(void);
 /* Number of usable CUDA devices (0 = none: every compute call will fail loudly). */
 int picard_device_count(void);
 const char* picard_status_string(int status); /* Display text of error.rs:44-74 */
+/* The library keeps up to 4 GiB of device memory (temporaries <= 1 GiB each) cached between calls because driver allocator
+ * calls are slow on these hosts; this returns it to the driver. */
+void picard_release_cache(void);
 
 /* ---- config (config.rs) --------------------------------------------------------------------------- */
 void picard_config_default(picard_config_t* cfg);                                  /* config.rs:64-85 */

@@ -12,7 +12,7 @@ dp = C.POINTER(C.c_double)
 
 # every symbol include/picard_b200.h declares (tests check the library exports all of them)
 EXPORTED = [
-    "picard_abi_version", "picard_device_count", "picard_status_string", "picard_config_default", "picard_config_validate",
+    "picard_abi_version", "picard_device_count", "picard_status_string", "picard_release_cache", "picard_config_default", "picard_config_validate",
     "picard_fit", "picard_fit_device", "picard_transform", "picard_result_free", "picard_core_create", "picard_core_run",
     "picard_core_reset", "picard_core_state", "picard_core_stats", "picard_core_destroy", "picard_eval_moments", "picard_eval_moments_device",
     "picard_eval_point", "picard_matrix_exp", "picard_sln_det", "picard_sym_decorrelation", "picard_compute_direction",
@@ -82,5 +82,6 @@ def lib():
         L.picard_config_default.restype = None
         L.picard_core_destroy.restype = None
         L.picard_comm_destroy.restype = None
+        L.picard_release_cache.restype = None
         _lib = L
     return _lib

@@ -75,6 +75,8 @@ const char* picard_status_string(int status) {
   }
 }
 
+void picard_release_cache(void) { dev_cache_release(); }
+
 void picard_config_default(picard_config_t* cfg) { if (cfg) config_default(cfg); }
 
 int picard_config_validate(const picard_config_t* cfg, char* err, size_t errlen) {
@@ -281,12 +283,12 @@ int picard_sym_decorrelation(const double* w, int64_t n64, double* out, int32_t 
     DeviceGuard guard(device);
     const int n = (int)n64;
     const size_t nn = (size_t)n * n;
-    DevBuf<double> buf(6 * nn + n);
+    DevBuf<double> win(nn), wout(nn), work(small::sym_decorrelation_work(n));
     DevBuf<int> st(1);
-    PICARD_CUDA(cudaMemcpy(buf.p, w, sizeof(double) * nn, cudaMemcpyHostToDevice));
-    small::sym_decorrelation(buf.p, n, buf.p + nn, buf.p + 5 * nn + n, st.p, 0);
+    PICARD_CUDA(cudaMemcpy(win.p, w, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    small::sym_decorrelation(win.p, n, work.p, wout.p, st.p, 0);
     PICARD_CUDA(cudaMemcpy(&status, st.p, sizeof(int), cudaMemcpyDeviceToHost));
-    PICARD_CUDA(cudaMemcpy(out, buf.p + 5 * nn + n, sizeof(double) * nn, cudaMemcpyDeviceToHost));
+    PICARD_CUDA(cudaMemcpy(out, wout.p, sizeof(double) * nn, cudaMemcpyDeviceToHost));
   });
   return rc != PICARD_OK ? rc : status;
 }

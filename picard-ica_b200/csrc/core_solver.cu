@@ -10,7 +10,88 @@
 //     (core.rs:317-329) and the initial loss (core.rs:185) need no extra pass.
 #include "engine.cuh"
 
+#include <chrono>
+#include <map>
+#include <mutex>
+
 namespace picard {
+
+double trace_now_ms() {
+  static const bool on = getenv("PICARD_TRACE") != nullptr;
+  if (!on) return -1.0;
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+void trace_slow(const char* what, size_t bytes, double t0_ms) {
+  if (t0_ms < 0) return;
+  const double dt = trace_now_ms() - t0_ms;
+  if (dt > 5.0) fprintf(stderr, "[picard trace]     slow %s of %.1f MB: %.1f ms\n", what, bytes / 1048576.0, dt);
+}
+
+namespace {
+struct DevCache {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_blocks;  // (device, capacity) -> block
+  size_t cached_bytes = 0;
+};
+DevCache& dev_cache() { static DevCache* c = new DevCache(); return *c; }  // leaked on purpose: no destructor order issues at exit
+constexpr size_t kCacheMaxBlock = (size_t)1 << 30, kCacheMaxTotal = (size_t)4 << 30;
+}  // namespace
+
+void* dev_alloc(size_t bytes, size_t* capacity) {
+  const size_t want = (bytes + 511) & ~(size_t)511;
+  int dev = 0;
+  PICARD_CUDA(cudaGetDevice(&dev));
+  if (want <= kCacheMaxBlock) {
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.free_blocks.lower_bound({dev, want});
+    if (it != c.free_blocks.end() && it->first.first == dev && it->first.second <= 2 * want + 4096) {
+      void* p = it->second;
+      *capacity = it->first.second;
+      c.cached_bytes -= it->first.second;
+      c.free_blocks.erase(it);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  const double t0 = trace_now_ms();
+  PICARD_CUDA(cudaMalloc(&p, want));
+  trace_slow("cudaMalloc", want, t0);
+  *capacity = want;
+  return p;
+}
+
+void dev_free(void* p, size_t capacity) {
+  if (!p) return;
+  if (capacity <= kCacheMaxBlock) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess) {
+      DevCache& c = dev_cache();
+      std::lock_guard<std::mutex> lk(c.mu);
+      if (c.cached_bytes + capacity <= kCacheMaxTotal) {
+        c.free_blocks.insert({{dev, capacity}, p});
+        c.cached_bytes += capacity;
+        return;
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  const double t0 = trace_now_ms();
+  cudaFree(p);
+  trace_slow("cudaFree", capacity, t0);
+}
+
+void dev_cache_release() {
+  DevCache& c = dev_cache();
+  std::lock_guard<std::mutex> lk(c.mu);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (auto& kv : c.free_blocks) { cudaSetDevice(kv.first.first); cudaFree(kv.second); }
+  c.free_blocks.clear();
+  c.cached_bytes = 0;
+  if (prev >= 0) cudaSetDevice(prev);
+}
 
 DeviceGuard::DeviceGuard(int dev) {
   int count = 0;
@@ -264,7 +345,7 @@ int64_t CoreSolver::run(int64_t max_new) {
 void CoreSolver::fastica(int64_t iters, double* w_host) {
   const int n = dims_.n;
   const size_t nn = (size_t)n * n;
-  DevBuf<double> work(4 * nn + n), tmp(nn);
+  DevBuf<double> work(small::sym_decorrelation_work(n)), tmp(nn);
   DevBuf<int> d_status(1);
   auto decorrelate = [&](const double* src, double* dst) {
     stats_.kernel_launches += small::sym_decorrelation(src, n, work.p, dst, d_status.p, st_);

@@ -23,6 +23,17 @@ int comm_size(const picard_comm* c);
 void comm_allreduce_sum(picard_comm* c, double* d_buf, size_t count, cudaStream_t st);
 void comm_allreduce_sum2(picard_comm* c, double* a, size_t na, double* b, size_t nb, cudaStream_t st);
 
+// PICARD_TRACE diagnostics: report driver allocator calls that take more than 5 ms
+double trace_now_ms();
+void trace_slow(const char* what, size_t bytes, double t0_ms);
+// Device memory for the library's temporaries.  cudaMalloc / cudaFree on the B200 hosts were measured at up to 0.4 s per
+// call after an idle period (50x the whitening kernels they bracket), so blocks up to 1 GiB are kept in a per-device
+// cache (at most 4 GiB in total) and reused; larger blocks (the N x T buffers) go straight to the driver.
+// dev_free synchronises the device first, like cudaFree does, so a block is never reused while work on it is in flight.
+void* dev_alloc(size_t bytes, size_t* capacity);
+void dev_free(void* p, size_t capacity);
+void dev_cache_release();  // return every cached block to the driver
+
 // ---- RAII device / pinned buffers
 template <typename T>
 struct DevBuf {
@@ -32,15 +43,22 @@ struct DevBuf {
   explicit DevBuf(size_t count) { alloc(count); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-  DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = 0; o.cap = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = 0; o.cap = 0; }
+    return *this;
+  }
   ~DevBuf() { release(); }
+  size_t cap = 0;  // bytes of the underlying block (>= sizeof(T) * n: blocks come from the cache below)
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) PICARD_CUDA(cudaMalloc(&p, sizeof(T) * count));
+    if (count) p = static_cast<T*>(dev_alloc(sizeof(T) * count, &cap));
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() {
+    if (p) dev_free(p, cap);
+    p = nullptr; n = 0; cap = 0;
+  }
   void zero(cudaStream_t st) { if (p) PICARD_CUDA(cudaMemsetAsync(p, 0, sizeof(T) * n, st)); }
 };
 template <typename T>

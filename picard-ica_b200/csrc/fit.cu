@@ -115,7 +115,8 @@ void center_whiten_device(const double* d_x, int nf, int64_t t_local, int64_t ld
   // symmetric eigenproblem of X_c X_c^T = U S^2 U^T: a SYRK-shaped pass (the moments kernel with psi(y) = y,
   // W = I, bias = mean) + one allreduce + a single-CTA Jacobi eigensolver.
   const size_t nn = (size_t)nf * nf;
-  DevBuf<double> eye(nn), mom((size_t)mom_size(nf) + MOM_EXTRA), partial(pass_workspace_doubles(nf, sm_count)), V(nn), ev((size_t)nf);
+  DevBuf<double> eye(nn), mom((size_t)mom_size(nf) + MOM_EXTRA), partial(pass_workspace_doubles(nf, sm_count)), V(nn), ev((size_t)nf),
+      eig_scratch(nn + 8);
   mark("whiten: allocations");
   stats->kernel_launches += small::set_identity(eye.p, nf, st);
   PassLaunch L;
@@ -125,7 +126,7 @@ void center_whiten_device(const double* d_x, int nf, int64_t t_local, int64_t ld
   stats->kernel_launches += launch_pass(L);
   mark("whiten: covariance pass");
   comm_allreduce_sum(comm, mom.p + mom_off_gr(nf), nn, st);
-  stats->kernel_launches += small::jacobi_eigh(mom.p + mom_off_gr(nf), nf, V.p, ev.p, st);
+  stats->kernel_launches += small::jacobi_eigh(mom.p + mom_off_gr(nf), nf, V.p, ev.p, eig_scratch.p, st);
   mark("whiten: eigensolver");
   std::vector<double> evals((size_t)nf), U(nn);
   PICARD_CUDA(cudaMemcpyAsync(evals.data(), ev.p, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
@@ -355,7 +356,7 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
     if (!cfg.has_seed) { std::random_device rd; seed = ((uint64_t)rd() << 32) ^ rd(); }
     std::vector<double> g((size_t)nc * nc);
     randn_fill(seed, g.data(), g.size());
-    DevBuf<double> dg((size_t)nc * nc), dwork(4 * (size_t)nc * nc + nc), dout((size_t)nc * nc);
+    DevBuf<double> dg((size_t)nc * nc), dwork(small::sym_decorrelation_work(nc)), dout((size_t)nc * nc);
     DevBuf<int> dst(1);
     PICARD_CUDA(cudaMemcpyAsync(dg.p, g.data(), sizeof(double) * nc * nc, cudaMemcpyHostToDevice, st));
     stats.kernel_launches += small::sym_decorrelation(dg.p, nc, dwork.p, dout.p, dst.p, st);

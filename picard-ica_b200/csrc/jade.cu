@@ -331,7 +331,7 @@ void jade_device(const double* d_x, int n, int64_t t_local, int64_t ld, double t
   const bool talk = verbose && (!comm || comm_rank(comm) == 0);
   const int n_pairs = n * (n + 1) / 2;
   const int m_pad = (n_pairs + 31) / 32 * 32;
-  DevBuf<double> rot((size_t)n * n * m_pad), V((size_t)n * n), work(4 * (size_t)n * n + n), W((size_t)n * n);
+  DevBuf<double> rot((size_t)n * n * m_pad), V((size_t)n * n), work(small::sym_decorrelation_work(n)), W((size_t)n * n);
   DevBuf<int> d_sweeps(1), d_status(1);
   rot.zero(st);
   cumulants_device(d_x, n, t_local, ld, t_total, comm, sm_count, st, nullptr, rot.p, m_pad, stats);

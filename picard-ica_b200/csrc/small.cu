@@ -619,8 +619,9 @@ __global__ void __launch_bounds__(BT1) jacobi_kernel(double* A, int n, double* V
 // A (n x n, symmetric, destroyed), Z (n x n work), V out: eigenvectors in COLUMNS, evals ascending.
 // ---------------------------------------------------------------------------------------------------
 constexpr int EIG_MAX_N = 512;
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __global__ void __launch_bounds__(BT1) tridiag_ql_kernel(double* __restrict__ A, int n, double* __restrict__ Z, double* __restrict__ V,
-                                                         double* __restrict__ evals) {
+                                                         double* __restrict__ evals, unsigned long long* __restrict__ stamps) {
   __shared__ double sh[33];
   __shared__ double d[EIG_MAX_N], e[EIG_MAX_N], v[EIG_MAX_N], q[EIG_MAX_N], cs[EIG_MAX_N], sn[EIG_MAX_N];
   __shared__ int rank_of[EIG_MAX_N];
@@ -628,6 +629,7 @@ __global__ void __launch_bounds__(BT1) tridiag_ql_kernel(double* __restrict__ A,
   __shared__ int s_int[4];
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
 
+  if (stamps && threadIdx.x == 0) stamps[0] = gtimer();
   // ---- phase 1: A = Q T Q^T, reflector k annihilates A[k+2.., k]; v_k kept in column k (rows k+1..), beta_k in q? no: in cs[]
   for (int k = 0; k + 2 < n; ++k) {
     const int m = n - k - 1;  // trailing block A[k+1.., k+1..]
@@ -675,6 +677,7 @@ __global__ void __launch_bounds__(BT1) tridiag_ql_kernel(double* __restrict__ A,
     d[n - 1] = A[(size_t)(n - 1) * n + (n - 1)];
     e[n - 1] = 0.0;
   }
+  if (stamps && threadIdx.x == 0) stamps[1] = gtimer();
   // ---- phase 2: Z = Q = H_0 H_1 ... H_{n-3}, accumulated backwards
   for (int idx = tid; idx < n * n; idx += nt) Z[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
   __syncthreads();
@@ -702,6 +705,7 @@ __global__ void __launch_bounds__(BT1) tridiag_ql_kernel(double* __restrict__ A,
   __syncthreads();
   double* Zt = V;
 
+  if (stamps && threadIdx.x == 0) stamps[2] = gtimer();
   // ---- phase 3: implicit QL on (d, e), rotations applied to rows of Zt (tql2)
   const double eps = 2.220446049250313e-16;
   if (tid == 0) { s_scal[0] = 0.0 /* f */; s_scal[1] = 0.0 /* tst1 */; }
@@ -767,6 +771,7 @@ __global__ void __launch_bounds__(BT1) tridiag_ql_kernel(double* __restrict__ A,
     if (tid == 0) { d[l] += s_scal[0]; e[l] = 0.0; }
     __syncthreads();
   }
+  if (stamps && threadIdx.x == 0) stamps[3] = gtimer();
   // ---- ascending order by rank (ties by index), eigenvectors to the COLUMNS of V via Z as scratch
   for (int i = tid; i < n; i += nt) {
     int r = 0;
@@ -889,24 +894,27 @@ int sln_det(const double* A, int n, double* work, double* out2, cudaStream_t st)
   return 1;
 }
 
-int jacobi_eigh(double* A, int n, double* V, double* evals, cudaStream_t st) {
+int jacobi_eigh(double* A, int n, double* V, double* evals, double* scratch, cudaStream_t st) {
   if (n > EIG_MAX_N) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: eigendecomposition supports n <= 512");
   if (n > 32) {  // Householder + implicit QL: O(n^3) data-parallel work, only the O(n^2) QL recurrence is sequential
-    double* z = nullptr;
-    PICARD_CUDA(cudaMallocAsync(&z, sizeof(double) * (size_t)n * n, st));
-    tridiag_ql_kernel<<<1, BT1, 0, st>>>(A, n, z, V, evals);
+    double* z = scratch;  // caller-provided: n^2 + 8 doubles (no allocation here: driver allocator calls after an idle period
+                          // were measured at up to ~1 s on the B200 hosts, 100x the kernel itself)
+    unsigned long long* stamps = getenv("PICARD_TRACE") ? reinterpret_cast<unsigned long long*>(z + (size_t)n * n) : nullptr;
+    tridiag_ql_kernel<<<1, BT1, 0, st>>>(A, n, z, V, evals, stamps);
     LAUNCH_CHECK();
-    PICARD_CUDA(cudaFreeAsync(z, st));
+    if (stamps) {
+      unsigned long long h[4];
+      PICARD_CUDA(cudaMemcpyAsync(h, stamps, sizeof h, cudaMemcpyDeviceToHost, st));
+      PICARD_CUDA(cudaStreamSynchronize(st));
+      fprintf(stderr, "[picard trace]     eigh n=%d: tridiag %.3f ms, accumulate Q %.3f ms, QL %.3f ms\n", n, (h[1] - h[0]) * 1e-6,
+              (h[2] - h[1]) * 1e-6, (h[3] - h[2]) * 1e-6);
+    }
     return 1;
   }
-  // tmp for the final column permutation: reuse the tail of the caller's buffers is error-prone; allocate async
-  double* tmp = nullptr;
-  PICARD_CUDA(cudaMallocAsync(&tmp, sizeof(double) * (size_t)n * n, st));
   int threads = n * n >= 1024 ? 1024 : ((n * n + 31) / 32) * 32;
   if (threads < 32) threads = 32;
-  jacobi_kernel<<<1, threads, 0, st>>>(A, n, V, evals, tmp);
+  jacobi_kernel<<<1, threads, 0, st>>>(A, n, V, evals, scratch);
   LAUNCH_CHECK();
-  PICARD_CUDA(cudaFreeAsync(tmp, st));
   return 1;
 }
 
@@ -935,8 +943,9 @@ int sym_decorrelation(const double* W, int n, double* work, double* out, int* st
   double* scaled = work + 2 * (size_t)n * n;
   double* t2 = work + 3 * (size_t)n * n;
   double* ev = work + 4 * (size_t)n * n;
+  double* scratch = ev + n + (n & 1);  // n^2 + 8 doubles for the eigensolver
   int launches = matmul(W, W, wwt, n, true, 1.0, false, st);
-  launches += jacobi_eigh(wwt, n, U, ev, st);
+  launches += jacobi_eigh(wwt, n, U, ev, scratch, st);
   int threads = n * n >= 1024 ? 1024 : ((n * n + 31) / 32) * 32;
   symdecor_scale_kernel<<<1, threads, 0, st>>>(U, ev, n, scaled, status_dev);
   LAUNCH_CHECK();

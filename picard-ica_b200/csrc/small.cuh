@@ -88,9 +88,12 @@ int fastica_matrix(const double* mom, int n, double t_total, const double* W, do
 
 // ---- symmetric eigendecomposition, cyclic Jacobi, single CTA (K7): A (n x n, destroyed), eigenvalues
 // ascending in evals, eigenvectors in the COLUMNS of V.
-int jacobi_eigh(double* A, int n, double* V, double* evals, cudaStream_t st);
+// scratch: n^2 + 8 doubles.
+int jacobi_eigh(double* A, int n, double* V, double* evals, double* scratch, cudaStream_t st);
 // sym_decorrelation (math.rs:12-33): out = (W W^T)^{-1/2} W ; *status_dev: 0 ok, 2 singular (min eig < 1e-10)
-int sym_decorrelation(const double* W, int n, double* work /* >= 4 n^2 + n */, double* out, int* status_dev, cudaStream_t st);
+int sym_decorrelation(const double* W, int n, double* work /* >= sym_decorrelation_work(n) doubles */, double* out, int* status_dev,
+                      cudaStream_t st);
+inline size_t sym_decorrelation_work(int n) { return 5 * (size_t)n * n + 2 * (size_t)n + 16; }
 
 }  // namespace small
 }  // namespace picard

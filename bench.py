@@ -43,6 +43,14 @@ WORKLOADS = {
     "c2": dict(n=64, t=1_000_000, ortho=True, extended=True, kind=0, alpha=1.0, n_laplace=32,
                desc="N=64,T=1e6 f64 Picard-O extended tanh, mixed Laplace/uniform sources"),
     "tiny": dict(n=16, t=200_000, ortho=True, extended=True, kind=0, alpha=1.0, n_laplace=8, desc="N=16,T=2e5 (debug)"),
+    # the other BASELINE configs: parity-test cases, runnable here for the record (profiles/), not the headline bench line
+    "c1": dict(n=3, t=10_000, ortho=False, extended=False, kind=0, alpha=1.0, n_laplace=3,
+               desc="N=3,T=1e4 f64 Picard tanh non-ortho, Laplace sources (reference bench case)"),
+    "c4": dict(n=256, t=50_000_000, ortho=False, extended=False, kind=1, alpha=0.1, n_laplace=256, per_gpu_t=6_250_000,
+               desc="N=256,T=5e7 f64 Picard non-ortho exp(alpha=0.1), Laplace sources, 8xB200 sharded "
+                    "(with fewer GPUs the per-GPU shard of 6.25e6 samples is kept and T shrinks)"),
+    "c5": dict(n=32, t=1_000_000, ortho=True, extended=True, kind=0, alpha=1.0, n_laplace=16, jade_it=50,
+               desc="N=32,T=1e6 f64 jade_it=50 warm start then Picard-O extended (JADE runs inside the e2e fit)"),
 }
 FP64_PEAK_TFLOPS = 37.19  # measured by us on this pool's B200 (profiles/microbench/fp64_pipes_r01.jsonl, DMMA m8n8k4);
 #                           MEASURED_PEAKS.json has no FP64 figure
@@ -202,6 +210,8 @@ def _main(out):
 
     lib = _ffi.lib()
     n, t_total = wl["n"], wl["t"]
+    if "per_gpu_t" in wl and world * wl["per_gpu_t"] < t_total:
+        t_total = world * wl["per_gpu_t"]  # c4 is specified for 8 GPUs: keep its per-GPU shard when fewer are available
     t0, t1 = shard_range(t_total, rank, world)
     t_local = t1 - t0
     ld = (t_local + 15) // 16 * 16
@@ -273,7 +283,7 @@ def _main(out):
     # ---- roofline of the dominant kernel: the fused pass (falls back to grad / loss variants if none ran)
     n2t = float(n) * n * t_local
     cand = [("fused", 4.0 * n2t, d["fused_passes"], d["pass_ms_fused"]), ("grad", 4.0 * n2t, d["grad_passes"], d["pass_ms_grad"]),
-            ("loss", 2.0 * n2t, d["loss_passes"], d["pass_ms_loss"]), ("grady", 2.0 * n2t, d["grady_passes"], d["pass_ms_grady"])]
+            ("loss", 2.0 * n2t, d["loss_passes"], d["pass_ms_loss"]), ("grady", (2.0 if wl["ortho"] else 4.0) * n2t, d["grady_passes"], d["pass_ms_grady"])]
     cand = [c for c in cand if c[2] > 0 and c[3] > 0]
     roof = None
     if cand:
@@ -306,7 +316,8 @@ def _main(out):
         del x_dev
         torch.cuda.empty_cache()
         xh = x_host.numpy()
-        cfg2 = P.PicardConfig(density=cfg.density, ortho=wl["ortho"], extended=wl["extended"], w_init=w0, comm=comm, device=local_rank)
+        cfg2 = P.PicardConfig(density=cfg.density, ortho=wl["ortho"], extended=wl["extended"], w_init=None if "jade_it" in wl else w0,
+                              jade_it=wl.get("jade_it"), comm=comm, device=local_rank)
         os.environ.setdefault("PICARD_TRACE", "1")  # stage timings of every e2e call on stderr (a few extra stream syncs)
         runs = []
         for _rep in range(3):  # three complete calls; the median is reported, all three are listed

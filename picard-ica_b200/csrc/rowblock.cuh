@@ -12,7 +12,7 @@
 //
 // Both are ROW-BLOCK partitioned: a CTA owns RP rows of the output (of Y', resp. of Gr / Hr) and all columns, so the
 // register-resident accumulators never exceed the register file whatever N is (N <= 256 here):
-//   loss : KP = 128 -> RP = 128 (1 row block) ; KP = 256 -> RP = 64 (4 row blocks)      [A fragments: 64 doubles / thread]
+//   loss : KP = 64 -> RP = 64 ; KP = 128 -> RP = 128 (1 row block) ; KP = 256 -> RP = 64 (4 row blocks)   [A fragments: <= 64 doubles / thread]
 //   grady: NP<=64 -> RP = NP ; 128 -> 128 (no H) / 64 (H) ; 256 -> 64 (no H) / 32 (H)   [accumulators: <= 64 doubles / thread]
 // Row blocks of one sample tile run on different SMs and read the same X / Y tile (L2 absorbs the re-reads); no data
 // is exchanged between CTAs.  Warps of a CTA are decoupled: stages are recycled by the last warp to release them.
@@ -72,19 +72,20 @@ static __global__ void reduce_rb_kernel(const double* __restrict__ partial, int 
 // -----------------------------------------------------------------------------------------------------
 template <int KP>
 struct RbLossGeom {
-  static_assert(KP == 128 || KP == 256, "register-resident A fragments are sized for KP = 128 or 256");
+  static_assert(KP == 64 || KP == 128 || KP == 256, "register-resident A fragments are sized for KP = 64, 128 or 256");
   static constexpr int NWARPS = 8;
   static constexpr int NTHREADS = NWARPS * 32;
   static constexpr int MB = KP == 128 ? 2 : 1;   // 8-row blocks per warp: MB * KP / 4 = 64 A-fragment doubles per thread
   static constexpr int RP = 8 * MB * NWARPS;     // rows of Y' per CTA
   static constexpr int KS = KP / 4;              // k-steps
   static constexpr int BT = 16;
-  static constexpr int STAGES = KP == 128 ? 6 : 4;
+  static constexpr int STAGES = KP == 256 ? 4 : 6;
+  static constexpr int MIN_BLOCKS = KP == 64 ? 2 : 1;  // KP = 64: 16 A-fragment doubles per thread, two CTAs per SM
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * KP * BT * 8 + (size_t)dmath::TAB_DOUBLES * 8 + 128;
 };
 
 template <int KP, int DENS, int MODE, bool WANT_SQ>
-__global__ void __launch_bounds__(RbLossGeom<KP>::NTHREADS, 1)
+__global__ void __launch_bounds__(RbLossGeom<KP>::NTHREADS, RbLossGeom<KP>::MIN_BLOCKS)
 rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, const int nrb) {
   using G = RbLossGeom<KP>;
   constexpr bool APPLY = (MODE == PASS_APPLY);

@@ -57,7 +57,9 @@ FP64_PEAK_TFLOPS = 37.19  # measured by us on this pool's B200 (profiles/microbe
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """Samples SM clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line).  NVML in-process
+    (nvidia_ml_py) when available: spawning nvidia-smi every 100 ms was measured to stall the solver's kernel launches
+    (driver locks) by up to 1 ms per line-search try; falls back to nvidia-smi at a 1 s period."""
 
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
@@ -65,31 +67,66 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
+        self.source = "nvml"
         self._halt = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu_index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+            self.source = "nvidia-smi"
 
-    def run(self):
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if i < len(ids) and ids[i].isdigit():
+                return int(ids[i])
+        return i
+
+    def _sample_nvml(self):
+        nv = self._nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for nm, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20)):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _sample_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for nm, v in zip(names, out[2:]):
+            if v.strip().lower() == "active":
+                self.reasons.add(nm)
+
+    def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if v.strip().lower() == "active":
-                        self.reasons.add(nm)
+                if self._h is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.05 if self._h is not None else 1.0)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=5)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "source": self.source}
 
 
 def host_inputs(n):

@@ -251,7 +251,7 @@ int picard_matrix_exp(const double* a, int64_t n64, double* out, int32_t device)
     DeviceGuard guard(device);
     const int n = (int)n64;
     const size_t nn = (size_t)n * n;
-    DevBuf<double> buf(8 * nn + 64);
+    DevBuf<double> buf(8 * nn + small::EXPM_SLOTS);
     double* b = buf.p;
     small::ExpmWork w{b + nn, b + 2 * nn, b + 3 * nn, b + 4 * nn, b + 5 * nn, b + 7 * nn};
     PICARD_CUDA(cudaMemcpy(b, a, sizeof(double) * nn, cudaMemcpyHostToDevice));

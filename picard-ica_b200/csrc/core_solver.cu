@@ -17,7 +17,7 @@
 namespace picard {
 
 double trace_now_ms() {
-  static const bool on = getenv("PICARD_TRACE") != nullptr;
+  static const bool on = getenv("PICARD_TRACE") != nullptr || getenv("PICARD_TRACE_TRY") != nullptr;
   if (!on) return -1.0;
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -138,7 +138,7 @@ CoreSolver::CoreSolver(const double* d_x, int n, int64_t t_local, int64_t ldx, c
   const size_t oW = take(nn), oWt = take(nn), oM = take(nn), oD = take(nn), oC = take(nn), oG = take(nn), oGt = take(nn),
                oGo = take(nn), oH = take(nn), oho = take(n), osg = take(n), oos = take(n), oSp = take(nn), oq = take(nn),
                oms = take(nn * dims_.m), omy = take(nn * dims_.m), omr = take(2 * (size_t)dims_.m), omc = take(msz), omt = take(msz),
-               olu = take(nn), oAs = take(nn), ot0 = take(nn), ot1 = take(nn), or0 = take(nn), or1 = take(nn), osl = take(32);
+               olu = take(nn), oAs = take(nn), ot0 = take(nn), ot1 = take(nn), or0 = take(nn), or1 = take(nn), osl = take(small::EXPM_SLOTS);
   store_.alloc(total);
   store_.zero(st_);
   double* b = store_.p;
@@ -227,6 +227,14 @@ void CoreSolver::fetch_scalars() {
 void CoreSolver::try_point(double alpha, bool speculate) {
   const int n = dims_.n;
   stats_.ls_tries++;
+  static const bool prof = getenv("PICARD_TRACE_TRY") != nullptr;  // diagnostics: where a line-search try spends its time
+  static cudaEvent_t pe[4];
+  static bool pe_init = false;
+  static double acc_ms[4] = {0, 0, 0, 0};
+  static long acc_n = 0;
+  const double w0 = prof ? trace_now_ms() : 0.0;
+  if (prof && !pe_init) { for (auto& e : pe) cudaEventCreate(&e); pe_init = true; }
+  if (prof) cudaEventRecord(pe[0], st_);
   if (dims_.ortho) {  // W' = expm(alpha D) W in one cooperative kernel (core.rs:119,125)
     stats_.kernel_launches += small::matrix_exp(D_, alpha, sc_host_.p->norm_d, n, ew_, nullptr, st_, W_, Wt_);
   } else {
@@ -235,9 +243,21 @@ void CoreSolver::try_point(double alpha, bool speculate) {
   }
   if (!dims_.ortho)  // -log|det W'| term of the loss (core.rs:51-70)
     stats_.kernel_launches += small::sln_det(Wt_, n, lu_work_, mom_trial_ + mom_size(n), st_);
+  static double host_enq_ms = 0.0;
+  if (prof) { host_enq_ms += trace_now_ms() - w0; cudaEventRecord(pe[1], st_); }
   pass(Wt_, speculate ? PASS_FUSED : PASS_LOSS, mom_trial_);                                      // core.rs:124,127
+  if (prof) cudaEventRecord(pe[2], st_);
   stats_.kernel_launches += small::loss_from_moments(dims_, mom_trial_, signs_, sc_dev_.p, 0, st_);
+  if (prof) cudaEventRecord(pe[3], st_);
   fetch_scalars();
+  if (prof) {
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, pe[0], pe[1]); cudaEventElapsedTime(&b, pe[1], pe[2]); cudaEventElapsedTime(&c, pe[2], pe[3]);
+    acc_ms[0] += a; acc_ms[1] += b; acc_ms[2] += c; acc_ms[3] += trace_now_ms() - w0; ++acc_n;
+    if (acc_n % 16 == 0)
+      fprintf(stderr, "[picard trace] try: transform %.3f ms (host enqueue %.3f ms), pass+reduce(+allreduce) %.3f ms, loss kernel %.3f ms, host wall %.3f ms (avg of %ld)\n",
+              acc_ms[0] / acc_n, host_enq_ms / acc_n, acc_ms[1] / acc_n, acc_ms[2] / acc_n, acc_ms[3] / acc_n, acc_n);
+  }
 }
 
 int64_t CoreSolver::run(int64_t max_new) {

@@ -3,11 +3,7 @@
 
 #include <cmath>
 
-#include <cooperative_groups.h>
-
 #include "pass.cuh"  // moment-buffer layout helpers
-
-namespace cg = cooperative_groups;
 
 namespace picard {
 namespace small {
@@ -385,86 +381,144 @@ __global__ void __launch_bounds__(256) matmul_kernel(const double* A, const doub
 }
 
 // ---------------------------------------------------------------------------------------------------
-// matrix_exp (math.rs:38-74) as ONE cooperative kernel: scaling, Taylor terms with the reference's early exit
-// (max |term_k| < 1e-16, <= 30 terms), s squarings, and optionally the product with W (core.rs:125) -- grid.sync()
-// between dependent steps instead of ~35 kernel launches per line-search try.  Work unit = 32 x 32 output tile.
+// matrix_exp (math.rs:38-74) [+ W' = expm(alpha D) W, core.rs:125] as ONE kernel, ROW-partitioned: term_k = term_{k-1} A_s / k
+// only needs the same rows of term_{k-1}, so each CTA owns 8 rows of term / result (shared memory) and reads A_s
+// (= D alpha 2^-s, formed on the fly from D) through L2; products on DMMA.  The only cross-CTA dependency of the Taylor
+// loop is the reference's early exit on the GLOBAL max |term_k| < 1e-16: every CTA publishes its local max per term and
+// reads the others' (flags in global memory) -- no grid-wide barrier per term (grid.sync() cost ~10 us x ~13 terms in the
+// previous version).  Squarings (s > 0, rare) exchange the result through global memory with one barrier each.
+// Cooperative launch only for the co-residency guarantee of the flag waits.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) expm_coop_kernel(const double* __restrict__ D, double alpha, double scale, double first_norm, int s,
-                                                        int n, double* As, double* T0, double* T1, double* R0, double* R1, double* slots,
-                                                        double* out, const double* W, double* Wt) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ double sh[33];
-  const int nt = (n + 31) / 32, ntiles = nt * nt;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  // phase 0: A_s = D alpha / scale ; term_1 = A_s ; result = I + A_s
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
-    const double v = (D[e] * alpha) / scale;
-    As[e] = v; T1[e] = v;
-    R0[e] = ((e / n == e % n) ? 1.0 : 0.0) + v;
+constexpr int EXPM_ROWS = 8;
+constexpr int EXPM_MAX_CTAS = 32;
+
+// acc[t][e] (t < 4) += T (8 x n, shared, pitch P) * B (n x n, global; element transform (b * mul0) * mul1) for column blocks
+// cb = warp + 8 t; thread (j, c): rows c, columns 8 cb + 2 j + e.  B may have been written by other CTAs: plain coherent loads.
+// ldb: leading dimension of B (n for global matrices, the padded pitch for the shared-memory copy of A_s).
+__device__ __forceinline__ void rows_times(const double* T, int P, const double* B, int ldb, int n, double mul0, double mul1, double acc[4][2]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = lane & 3, c = lane >> 2;
+  const int ncb = (n + 7) >> 3;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll 8
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    const bool kok = k0 + j < n;
+    const double a = kok ? T[c * P + k0 + j] : 0.0;
+    double b[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int col = 8 * (warp + 8 * t) + c;
+      b[t] = (kok && warp + 8 * t < ncb && col < n) ? (B[(size_t)(k0 + j) * ldb + col] * mul0) * mul1 : 0.0;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (warp + 8 * t < ncb)  // warp-uniform
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a), "d"(b[t]));
   }
-  if (blockIdx.x == 0 && threadIdx.x < 32) slots[threadIdx.x] = 0.0;
-  grid.sync();
-  double* tp = T1; double* tn = T0;
-  double prev = first_norm;  // max |term_1| = max |D alpha| / scale (exact: scale is a power of two)
-  for (int k = 2; k <= 30; ++k) {
-    if (prev < 1e-16) break;  // the `break` of math.rs:63-65 (uniform: every thread reads the same value)
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int bi = tile / nt, bj = tile % nt;
-      double acc[2][2];
-      tile_mm<false>(tp, n, As, n, n, n, n, bi, bj, acc);
+}
+
+__global__ void __launch_bounds__(256) expm_rows_kernel(const double* __restrict__ D, double alpha, double inv_scale, double first_norm, int s,
+                                                        int n, double* flags, unsigned int* bar, double* Rg0, double* Rg1, double* out,
+                                                        const double* __restrict__ W, double* Wt, int as_in_smem) {
+  extern __shared__ double esm[];
+  __shared__ double sh[33];
+  const int P = n + 4, PA = n + 8;
+  double* Tc = esm; double* Tn = esm + EXPM_ROWS * P; double* R = esm + 2 * EXPM_ROWS * P;
+  double* Asm = esm + 3 * EXPM_ROWS * P;  // n x PA copy of A_s when it fits (n <= 128): B fragments at shared-memory latency
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, j = lane & 3, c = lane >> 2;
+  const int G = gridDim.x, row0 = blockIdx.x * EXPM_ROWS, ncb = (n + 7) >> 3;
+  // term_1 = A_s rows ; result = I + A_s   (A_s = (D alpha) / 2^s, math.rs:47-53)
+  for (int e = tid; e < EXPM_ROWS * n; e += blockDim.x) {
+    const int r = e / n, col = e % n, grow = row0 + r;
+    const double v = grow < n ? (D[(size_t)grow * n + col] * alpha) * inv_scale : 0.0;
+    Tc[r * P + col] = v;
+    R[r * P + col] = ((grow == col) ? 1.0 : 0.0) + v;
+  }
+  if (as_in_smem)
+    for (int e = tid; e < n * n; e += blockDim.x) Asm[(e / n) * PA + (e % n)] = (D[e] * alpha) * inv_scale;
+  __syncthreads();
+  const double* Bm = as_in_smem ? Asm : D;
+  const int ldb = as_in_smem ? PA : n;
+  const double m0 = as_in_smem ? 1.0 : alpha, m1 = as_in_smem ? 1.0 : inv_scale;
+  // Taylor terms.  The reference stops after the first term whose GLOBAL max is below 1e-16 (math.rs:58-66).  Term k is
+  // computed speculatively, then the published maxima of term k-1 (written one whole term ago: no waiting in practice)
+  // decide whether it exists; a term that does not exist is discarded, so the result is exactly the reference's sum.
+  if (!(first_norm < 1e-16)) {
+    for (int k = 2; k <= 30; ++k) {
+      double acc[4][2];
+      rows_times(Tc, P, Bm, ldb, n, m0, m1, acc);
+      if (k > 2) {
+        double v = 0.0;
+        if (tid < G) {
+          const volatile double* f = flags + (size_t)(k - 1) * G + tid;
+          do { v = *f; } while (v != v);  // NaN = not published yet
+        }
+        if (block_max(v, sh) < 1e-16) break;  // uniform over the whole grid: every CTA reduces the same published values
+      }
       double mx = 0.0;
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+      for (int t = 0; t < 4; ++t)
+        if (warp + 8 * t < ncb)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int i = bi * 32 + ty + 16 * a, j = bj * 32 + tx + 16 * b;
-          if (i < n && j < n) {
-            const double v = acc[a][b] / (double)k;
-            tn[(size_t)i * n + j] = v;
-            R0[(size_t)i * n + j] += v;
-            mx = fmax(mx, fabs(v));
+          for (int e = 0; e < 2; ++e) {
+            const int col = 8 * (warp + 8 * t) + 2 * j + e;
+            if (col < n) {
+              const double v = acc[t][e] / (double)k;
+              Tn[c * P + col] = v;
+              R[c * P + col] += v;
+              if (row0 + c < n) mx = fmax(mx, fabs(v));
+            }
           }
-        }
-      mx = block_max(mx, sh);
-      if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(&slots[k]), (unsigned long long)__double_as_longlong(mx));
+      mx = block_max(mx, sh);  // (contains the barriers that make Tn visible)
+      if (tid == 0) { *reinterpret_cast<volatile double*>(flags + (size_t)k * G + blockIdx.x) = mx; __threadfence(); }
+      double* t = Tc; Tc = Tn; Tn = t;
     }
-    grid.sync();
-    prev = *reinterpret_cast<volatile double*>(&slots[k]);
-    double* t = tp; tp = tn; tn = t;
   }
-  // squaring (math.rs:69-71)
-  double* cur = R0; double* nxt = R1;
+  // squaring (math.rs:69-71): result <- result * result, s times; the full result goes through global memory
+  double* Rg = Rg0; double* Rn = Rg1;
   for (int q = 0; q < s; ++q) {
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int bi = tile / nt, bj = tile % nt;
-      double acc[2][2];
-      tile_mm<false>(cur, n, cur, n, n, n, n, bi, bj, acc);
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int i = bi * 32 + ty + 16 * a, j = bj * 32 + tx + 16 * b;
-          if (i < n && j < n) nxt[(size_t)i * n + j] = acc[a][b];
-        }
+    for (int e = tid; e < EXPM_ROWS * n; e += blockDim.x) {
+      const int r = e / n, col = e % n;
+      if (row0 + r < n) Rg[(size_t)(row0 + r) * n + col] = R[r * P + col];
     }
-    grid.sync();
-    double* t = cur; cur = nxt; nxt = t;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(bar, 1u);
+      while (*reinterpret_cast<volatile unsigned int*>(bar) < (unsigned)(G * (q + 1))) {}
+      __threadfence();
+    }
+    __syncthreads();
+    double acc[4][2];
+    rows_times(R, P, Rg, n, n, 1.0, 1.0, acc);
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (warp + 8 * t < ncb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * (warp + 8 * t) + 2 * j + e;
+          if (col < n) R[c * P + col] = acc[t][e];
+        }
+    __syncthreads();
+    double* t = Rg; Rg = Rn; Rn = t;
   }
   if (out != nullptr)
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) out[e] = cur[e];
-  if (W != nullptr && Wt != nullptr) {  // W' = expm(alpha D) W   (core.rs:125)
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int bi = tile / nt, bj = tile % nt;
-      double acc[2][2];
-      tile_mm<false>(cur, n, W, n, n, n, n, bi, bj, acc);
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int i = bi * 32 + ty + 16 * a, j = bj * 32 + tx + 16 * b;
-          if (i < n && j < n) Wt[(size_t)i * n + j] = acc[a][b];
-        }
+    for (int e = tid; e < EXPM_ROWS * n; e += blockDim.x) {
+      const int r = e / n, col = e % n;
+      if (row0 + r < n) out[(size_t)(row0 + r) * n + col] = R[r * P + col];
     }
+  if (W != nullptr && Wt != nullptr) {  // W' rows = result rows * W   (core.rs:125)
+    double acc[4][2];
+    rows_times(R, P, W, n, n, 1.0, 1.0, acc);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (warp + 8 * t < ncb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * (warp + 8 * t) + 2 * j + e;
+          if (col < n && row0 + c < n) Wt[(size_t)(row0 + c) * n + col] = acc[t][e];
+        }
   }
 }
 
@@ -875,15 +929,27 @@ int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWo
     return launches;
   }
   int s = (int)std::fmax(std::ceil(std::log2(norm)), 0.0);
-  double scale = std::ldexp(1.0, s);
-  double first_norm = norm / scale;
-  const int nt = (n + 31) / 32;
-  int grid = nt * nt;
-  if (grid > 64) grid = 64;
-  double* res0 = w.res0; double* res1 = w.res1; double* As = w.As; double* t0 = w.term0; double* t1 = w.term1; double* slots = w.slots;
-  void* args[] = {(void*)&D, (void*)&alpha, (void*)&scale, (void*)&first_norm, (void*)&s, (void*)&n, (void*)&As, (void*)&t0, (void*)&t1,
-                  (void*)&res0, (void*)&res1, (void*)&slots, (void*)&out, (void*)&W, (void*)&Wt};
-  PICARD_CUDA(cudaLaunchCooperativeKernel((const void*)expm_coop_kernel, dim3(grid), dim3(256), args, 0, st));
+  double inv_scale = std::ldexp(1.0, -s);  // dividing by 2^s == multiplying by 2^-s, exactly
+  double first_norm = norm * inv_scale;
+  const int grid = (n + EXPM_ROWS - 1) / EXPM_ROWS;
+  if (grid > EXPM_MAX_CTAS) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: matrix_exp supports n <= 256");
+  int as_in_smem = n <= 128 ? 1 : 0;  // A_s (n x n) staged in shared memory when it fits
+  const size_t smem = sizeof(double) * (3 * EXPM_ROWS * (size_t)(n + 4) + (as_in_smem ? (size_t)n * (n + 8) : 0));
+  static bool configured = false;
+  if (!configured) {
+    PICARD_CUDA(cudaFuncSetAttribute(expm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(double) * (3 * EXPM_ROWS * (128 + 4) + 128 * (128 + 8)))));
+    configured = true;
+  }
+  // w.slots: [barrier counter (8 doubles)][flags: 31 x grid doubles]; all-ones bytes = NaN = "not published yet"
+  unsigned int* bar = reinterpret_cast<unsigned int*>(w.slots);
+  double* flags = w.slots + 8;
+  PICARD_CUDA(cudaMemsetAsync(bar, 0, sizeof(double) * 8, st));
+  PICARD_CUDA(cudaMemsetAsync(flags, 0xFF, sizeof(double) * 31 * (size_t)grid, st));
+  double* r0 = w.res0; double* r1 = w.res1;
+  void* args[] = {(void*)&D, (void*)&alpha, (void*)&inv_scale, (void*)&first_norm, (void*)&s, (void*)&n, (void*)&flags, (void*)&bar,
+                  (void*)&r0, (void*)&r1, (void*)&out, (void*)&W, (void*)&Wt, (void*)&as_in_smem};
+  PICARD_CUDA(cudaLaunchCooperativeKernel((const void*)expm_rows_kernel, dim3(grid), dim3(256), args, smem, st));
   return 1;
 }
 

@@ -73,7 +73,8 @@ int negate_into(const double* G, double* D, int64_t count, CoreScalars* sc, cuda
 int clear_memory(CoreScalars* sc, cudaStream_t st);
 
 // ---- matrix_exp (math.rs:38-74): out = expm(alpha * D). norm_d = max|D| known to the host.
-struct ExpmWork { double* As; double* term0; double* term1; double* res0; double* res1; double* slots; };
+struct ExpmWork { double* As; double* term0; double* term1; double* res0; double* res1; double* slots; };  // n^2 each; slots: EXPM_SLOTS
+constexpr int EXPM_SLOTS = 8 + 31 * 32;
 // One cooperative kernel.  out (may be NULL) = expm(alpha D); if W and Wt are given, Wt = expm(alpha D) W (core.rs:125).
 int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWork& w, double* out, cudaStream_t st,
                const double* W = nullptr, double* Wt = nullptr);

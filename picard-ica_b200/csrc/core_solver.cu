@@ -224,7 +224,7 @@ void CoreSolver::fetch_scalars() {
 }
 
 // One line-search try (core.rs:118-128): transform, W' = M W, pass at W', loss, accept flag -> scalars on host.
-void CoreSolver::try_point(double alpha, bool speculate) {
+void CoreSolver::try_point(double alpha, bool speculate, int try_index, int tries_planned) {
   const int n = dims_.n;
   stats_.ls_tries++;
   static const bool prof = getenv("PICARD_TRACE_TRY") != nullptr;  // diagnostics: where a line-search try spends its time
@@ -235,8 +235,16 @@ void CoreSolver::try_point(double alpha, bool speculate) {
   const double w0 = prof ? trace_now_ms() : 0.0;
   if (prof && !pe_init) { for (auto& e : pe) cudaEventCreate(&e); pe_init = true; }
   if (prof) cudaEventRecord(pe[0], st_);
-  if (dims_.ortho) {  // W' = expm(alpha D) W in one cooperative kernel (core.rs:119,125)
-    stats_.kernel_launches += small::matrix_exp(D_, alpha, sc_host_.p->norm_d, n, ew_, nullptr, st_, W_, Wt_);
+  w_try_ = Wt_;
+  if (dims_.ortho) {  // W' = expm(alpha D) W (core.rs:119,125)
+    if (try_index == 0) {  // every candidate alpha / 2^t of this search from one Taylor run (bit-identical to one run per try)
+      if (!wt_all_.p) wt_all_.alloc((size_t)small::EXPM_NC * n * n);
+      const int r = small::matrix_exp_candidates(D_, alpha, sc_host_.p->norm_d, n, tries_planned, ew_, W_, wt_all_.p, st_);
+      cand_ready_ = r > 0 ? r : 0;
+      if (r > 0) stats_.kernel_launches += 1;
+    }
+    if (try_index < cand_ready_) w_try_ = wt_all_.p + (size_t)try_index * n * n;
+    else stats_.kernel_launches += small::matrix_exp(D_, alpha, sc_host_.p->norm_d, n, ew_, nullptr, st_, W_, Wt_);
   } else {
     stats_.kernel_launches += small::eye_plus_scaled(D_, alpha, M_, n, st_);                      // core.rs:121
     stats_.kernel_launches += small::matmul(M_, W_, Wt_, n, false, 1.0, false, st_);              // core.rs:125
@@ -245,7 +253,7 @@ void CoreSolver::try_point(double alpha, bool speculate) {
     stats_.kernel_launches += small::sln_det(Wt_, n, lu_work_, mom_trial_ + mom_size(n), st_);
   static double host_enq_ms = 0.0;
   if (prof) { host_enq_ms += trace_now_ms() - w0; cudaEventRecord(pe[1], st_); }
-  pass(Wt_, speculate ? PASS_FUSED : PASS_LOSS, mom_trial_);                                      // core.rs:124,127
+  pass(w_try_, speculate ? PASS_FUSED : PASS_LOSS, mom_trial_);                                   // core.rs:124,127
   if (prof) cudaEventRecord(pe[2], st_);
   stats_.kernel_launches += small::loss_from_moments(dims_, mom_trial_, signs_, sc_dev_.p, 0, st_);
   if (prof) cudaEventRecord(pe[3], st_);
@@ -311,7 +319,7 @@ int64_t CoreSolver::run(int64_t max_new) {
     bool first_try_ok = false;
     for (int64_t t = 0; t < cfg_.ls_tries; ++t) {
       last_spec = !no_spec && t == 0 && speculate_next_;
-      try_point(alpha, last_spec);
+      try_point(alpha, last_spec, (int)t, (int)cfg_.ls_tries);
       if (sc_host_.p->accept) { success = true; first_try_ok = (t == 0); break; }
       alpha /= 2.0;
     }
@@ -322,15 +330,16 @@ int64_t CoreSolver::run(int64_t max_new) {
       alpha = 1.0;
       for (int t = 0; t < 10; ++t) {
         last_spec = false;
-        try_point(alpha, false);
+        try_point(alpha, false, t, 10);
         if (sc_host_.p->accept) { success = true; break; }
         alpha /= 2.0;
       }
     }
     // step = direction * alpha (on failure alpha has been halved once more: quirk Q2)
-    stats_.kernel_launches += small::accept_step(dims_, D_, alpha, Sprev_, Wt_, C_, (dims_.extended && cov_identity_) ? 1 : 0,
+    stats_.kernel_launches += small::accept_step(dims_, D_, alpha, Sprev_, w_try_, C_, (dims_.extended && cov_identity_) ? 1 : 0,
                                                  sc_dev_.p, st_);
-    std::swap(W_, Wt_);
+    if (w_try_ == Wt_) std::swap(W_, Wt_);
+    else PICARD_CUDA(cudaMemcpyAsync(W_, w_try_, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, st_));
     std::swap(mom_cur_, mom_trial_);
     have_cur_ = last_spec;
     speculate_next_ = first_try_ok;

@@ -116,7 +116,7 @@ class CoreSolver {
  private:
   void pass(const double* d_w, int mode, double* d_mom);
   void fetch_scalars();
-  void try_point(double alpha, bool speculate);
+  void try_point(double alpha, bool speculate, int try_index, int tries_planned);
 
   CoreDims dims_;
   picard_config_t cfg_;
@@ -132,6 +132,9 @@ class CoreSolver {
 
   DevBuf<double> store_;   // all N x N state in one allocation
   DevBuf<double> partial_;
+  DevBuf<double> wt_all_;  // W' of every candidate step of the current line search (one Taylor run, small::matrix_exp_candidates)
+  int cand_ready_ = 0;
+  double* w_try_ = nullptr;  // W' of the last evaluated try
   DevBuf<double> ybuf_;    // Y' of the last loss-only try (n x ldx_), empty when PICARD_FLAG_NO_Y_STORE or out of memory
   bool ybuf_valid_ = false;
   DevBuf<CoreScalars> sc_dev_;

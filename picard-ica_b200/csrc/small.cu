@@ -522,6 +522,117 @@ __global__ void __launch_bounds__(256) expm_rows_kernel(const double* __restrict
   }
 }
 
+// All candidate transforms of one backtracking line search from ONE Taylor run (core.rs:118-125 for alpha = a0 / 2^t,
+// t = 0 .. NC-1).  With s = 0 (max |a0 D| <= 1) the reference's series for candidate t is the a0 series with term k scaled
+// by 2^{-k t} -- EXACTLY, powers of two commute with every rounding -- and its early exit is the first k with
+// max |term_k| 2^{-k t} < 1e-16.  So one pass over the terms accumulates result_t = I + sum_k term_k 2^{-k t} for every t
+// in the reference's order (bit-identical to running the series per try), then W'_t = result_t W.  NT = 8-column blocks
+// per warp (2 for n <= 128, 4 for n <= 256).
+template <int NT>
+__global__ void __launch_bounds__(256) expm_multi_kernel(const double* __restrict__ D, double alpha, double first_norm, int n, int nc,
+                                                         double* flags, const double* __restrict__ W, double* Wt_all, int as_in_smem) {
+  extern __shared__ double esm[];
+  __shared__ double sh[33];
+  const int P = n + 4, PA = n + 8;
+  double* Tc = esm; double* Tn = esm + EXPM_ROWS * P;
+  double* Asm = esm + 2 * EXPM_ROWS * P;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, j = lane & 3, c = lane >> 2;
+  const int G = gridDim.x, row0 = blockIdx.x * EXPM_ROWS, ncb = (n + 7) >> 3;
+  for (int e = tid; e < EXPM_ROWS * n; e += blockDim.x) {
+    const int r = e / n, col = e % n, grow = row0 + r;
+    Tc[r * P + col] = grow < n ? D[(size_t)grow * n + col] * alpha : 0.0;
+  }
+  if (as_in_smem)
+    for (int e = tid; e < n * n; e += blockDim.x) Asm[(e / n) * PA + (e % n)] = D[e] * alpha;
+  __syncthreads();
+  const double* Bm = as_in_smem ? Asm : D;
+  const int ldb = as_in_smem ? PA : n;
+  const double m0 = as_in_smem ? 1.0 : alpha;
+  // per-thread result entries of every candidate: rows row0 + c, columns 8 (warp + 8 t') + 2 j + e
+  double rt[EXPM_NC][NT][2];
+  double pw[EXPM_NC];      // 2^{-k t} of the current k
+  double step[EXPM_NC];    // 2^{-t}
+  bool alive[EXPM_NC];
+#pragma unroll
+  for (int t = 0; t < EXPM_NC; ++t) {
+    step[t] = 1.0 / (double)(1u << t);
+    pw[t] = step[t];  // k = 1
+    alive[t] = t < nc && !(first_norm * pw[t] < 1e-16);  // exit test after term 1
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = 8 * (warp + 8 * tt) + 2 * j + e;
+        const double a1 = (col < n) ? Tc[c * P + col] : 0.0;
+        rt[t][tt][e] = ((row0 + c == col) ? 1.0 : 0.0) + a1 * pw[t];
+      }
+  }
+  for (int k = 2; k <= 30; ++k) {
+    double acc[4][2];
+    rows_times(Tc, P, Bm, ldb, n, m0, 1.0, acc);
+    if (k > 2) {  // the reference's `break` for each candidate, on the published global max of term k-1
+      double v = 0.0;
+      if (tid < G) {
+        const volatile double* f = flags + (size_t)(k - 1) * G + tid;
+        do { v = *f; } while (v != v);
+      }
+      const double gprev = block_max(v, sh);
+#pragma unroll
+      for (int t = 0; t < EXPM_NC; ++t)
+        if (alive[t] && gprev * pw[t] < 1e-16) alive[t] = false;  // pw[t] still holds 2^{-(k-1) t}
+    }
+    bool any = false;
+#pragma unroll
+    for (int t = 0; t < EXPM_NC; ++t) { pw[t] *= step[t]; any = any || alive[t]; }  // now 2^{-k t}
+    if (!any) break;  // uniform over the grid
+    double mx = 0.0;
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt)
+      if (warp + 8 * tt < ncb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * (warp + 8 * tt) + 2 * j + e;
+          if (col < n) {
+            const double v = acc[tt][e] / (double)k;
+            Tn[c * P + col] = v;
+#pragma unroll
+            for (int t = 0; t < EXPM_NC; ++t)
+              if (alive[t]) rt[t][tt][e] += v * pw[t];
+            if (row0 + c < n) mx = fmax(mx, fabs(v));
+          }
+        }
+    mx = block_max(mx, sh);
+    if (tid == 0) { *reinterpret_cast<volatile double*>(flags + (size_t)k * G + blockIdx.x) = mx; __threadfence(); }
+    double* tsw = Tc; Tc = Tn; Tn = tsw;
+  }
+  // W'_t rows = result_t rows * W
+#pragma unroll
+  for (int t = 0; t < EXPM_NC; ++t) {
+    if (t >= nc) break;
+    __syncthreads();
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt)
+      if (warp + 8 * tt < ncb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * (warp + 8 * tt) + 2 * j + e;
+          if (col < n) Tn[c * P + col] = rt[t][tt][e];
+        }
+    __syncthreads();
+    double acc[4][2];
+    rows_times(Tn, P, W, n, n, 1.0, 1.0, acc);
+    double* dst = Wt_all + (size_t)t * n * n;
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt)
+      if (warp + 8 * tt < ncb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * (warp + 8 * tt) + 2 * j + e;
+          if (col < n && row0 + c < n) dst[(size_t)(row0 + c) * n + col] = acc[tt][e];
+        }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // signed log-determinant: LU with partial pivoting, single CTA, in `work` (n x n)
 // ---------------------------------------------------------------------------------------------------
@@ -951,6 +1062,31 @@ int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWo
                   (void*)&r0, (void*)&r1, (void*)&out, (void*)&W, (void*)&Wt, (void*)&as_in_smem};
   PICARD_CUDA(cudaLaunchCooperativeKernel((const void*)expm_rows_kernel, dim3(grid), dim3(256), args, smem, st));
   return 1;
+}
+
+int matrix_exp_candidates(const double* D, double alpha0, double norm_d, int n, int n_cand, const ExpmWork& w, const double* W, double* Wt_all,
+                          cudaStream_t st) {
+  const double norm = norm_d * alpha0;
+  if (!(norm >= 1e-15) || norm > 1.0 || n_cand < 2 || n > 256) return -1;  // s > 0 or degenerate: the caller uses the per-try path
+  if (n_cand > EXPM_NC) n_cand = EXPM_NC;
+  double first_norm = norm;
+  const int grid = (n + EXPM_ROWS - 1) / EXPM_ROWS;
+  int as_in_smem = n <= 128 ? 1 : 0;
+  const size_t smem = sizeof(double) * (2 * EXPM_ROWS * (size_t)(n + 4) + (as_in_smem ? (size_t)n * (n + 8) : 0));
+  static bool configured = false;
+  if (!configured) {
+    const int mx = (int)(sizeof(double) * (2 * EXPM_ROWS * (128 + 4) + 128 * (128 + 8)));
+    PICARD_CUDA(cudaFuncSetAttribute(expm_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    PICARD_CUDA(cudaFuncSetAttribute(expm_multi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    configured = true;
+  }
+  double* flags = w.slots + 8;
+  PICARD_CUDA(cudaMemsetAsync(flags, 0xFF, sizeof(double) * 31 * (size_t)grid, st));
+  void* args[] = {(void*)&D, (void*)&alpha0, (void*)&first_norm, (void*)&n, (void*)&n_cand, (void*)&flags, (void*)&W, (void*)&Wt_all,
+                  (void*)&as_in_smem};
+  if (n <= 128) PICARD_CUDA(cudaLaunchCooperativeKernel((const void*)expm_multi_kernel<2>, dim3(grid), dim3(256), args, smem, st));
+  else PICARD_CUDA(cudaLaunchCooperativeKernel((const void*)expm_multi_kernel<4>, dim3(grid), dim3(256), args, smem, st));
+  return n_cand;
 }
 
 int sln_det(const double* A, int n, double* work, double* out2, cudaStream_t st) {

@@ -75,6 +75,12 @@ int clear_memory(CoreScalars* sc, cudaStream_t st);
 // ---- matrix_exp (math.rs:38-74): out = expm(alpha * D). norm_d = max|D| known to the host.
 struct ExpmWork { double* As; double* term0; double* term1; double* res0; double* res1; double* slots; };  // n^2 each; slots: EXPM_SLOTS
 constexpr int EXPM_SLOTS = 8 + 31 * 32;
+constexpr int EXPM_NC = 10;  // candidate steps per Taylor run
+// W'_t = expm(alpha0 / 2^t D) W for t = 0 .. n_cand-1 (<= 10) from one Taylor run (bit-identical to n_cand calls of matrix_exp).
+// Returns the number of candidates produced into Wt_all ([t][n][n]), or -1 when the case needs the per-try path
+// (max |alpha0 D| > 1, i.e. squarings, or a degenerate norm).
+int matrix_exp_candidates(const double* D, double alpha0, double norm_d, int n, int n_cand, const ExpmWork& w, const double* W, double* Wt_all,
+                          cudaStream_t st);
 // One cooperative kernel.  out (may be NULL) = expm(alpha D); if W and Wt are given, Wt = expm(alpha D) W (core.rs:125).
 int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWork& w, double* out, cudaStream_t st,
                const double* W = nullptr, double* Wt = nullptr);

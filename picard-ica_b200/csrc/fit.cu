@@ -133,8 +133,14 @@ void center_whiten_device(const double* d_x, int nf, int64_t t_local, int64_t ld
   PICARD_CUDA(cudaMemcpyAsync(U.data(), V.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
   PICARD_CUDA(cudaStreamSynchronize(st));
   // singular values descending = sqrt of eigenvalues descending (dgesvd order); min over the kept ones (whitening.rs:72-79)
+  // The eigenvalues of the Gram matrix carry rounding noise ~eps * lambda_max, so singular values below ~1e-7 sigma_max
+  // cannot be told from zero (the reference's SVD resolves them down to its absolute 1e-10): they are reported as singular.
+  const double noise_floor = 1e-14 * std::fmax(evals[nf - 1], 0.0);
   double min_sv = INFINITY;
-  for (int i = 0; i < nc; ++i) min_sv = std::fmin(min_sv, std::sqrt(std::fmax(evals[nf - 1 - i], 0.0)));
+  for (int i = 0; i < nc; ++i) {
+    const double ev = evals[nf - 1 - i];
+    min_sv = std::fmin(min_sv, ev > noise_floor ? std::sqrt(ev) : 0.0);
+  }
   if (!(min_sv >= 1e-10)) throw Error(PICARD_SINGULAR_MATRIX, "Singular matrix encountered during computation");
   const double scale = std::sqrt(t_total);  // whitening.rs:83
   k_host.assign((size_t)nc * nf, 0.0);

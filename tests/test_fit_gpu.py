@@ -210,3 +210,39 @@ def test_odd_t_and_strided_input():
     res = Picard.fit_with_config(x, PicardConfig(w_init=w0))
     ref = orc.fit(np.ascontiguousarray(x), orc.Config(w_init=w0))
     _cmp(res, ref)
+
+
+def test_tiny_shapes():
+    """Edge cases: a single partial tile (T < 16), one component, T = N (barely determined)."""
+    rng = np.random.default_rng(0)
+    x = rng.laplace(size=(2, 13))
+    w0 = _data.orthogonal(2, 43)
+    res = Picard.fit_with_config(x, PicardConfig(w_init=w0, max_iter=20))
+    ref = orc.fit(x, orc.Config(w_init=w0, max_iter=20))
+    assert res.sources.shape == (2, 13) and abs(res.n_iterations - ref.n_iterations) <= 1
+    np.testing.assert_allclose(res.sources @ res.sources.T / 13, np.eye(2), atol=1e-8)   # Picard-O keeps the whitened scale
+    one = Picard.fit_with_config(rng.laplace(size=(1, 100)), PicardConfig(max_iter=5))
+    assert one.unmixing.shape == (1, 1) and one.sources.shape == (1, 100)
+    np.testing.assert_allclose(np.mean(one.sources ** 2), 1.0, atol=1e-10)
+
+
+def test_more_features_than_samples_is_singular():
+    """n_components = min(n, p) (solver.rs:63); with T < N the centred data has rank < T, so whitening reports SingularMatrix
+    (whitening.rs:72-79) exactly like the reference."""
+    x = np.random.default_rng(1).standard_normal((6, 4))
+    with pytest.raises(PicardError.SingularMatrix):
+        Picard.fit(x)
+    with pytest.raises(orc.OracleError) as e:
+        orc.fit(x)
+    assert e.value.code == orc.SINGULAR
+
+
+def test_rectangular_whitening_and_transform_of_new_data():
+    x, a, _ = _data.mixture(10, 5000, seed=4, kind="laplace")
+    w0 = _data.orthogonal(4, 43)
+    res = Picard.fit_with_config(x, PicardConfig(n_components=4, w_init=w0, max_iter=100))
+    ref = orc.fit(x, orc.Config(n_components=4, w_init=w0, max_iter=100))
+    assert res.whitening.shape == (4, 10) and res.sources.shape == (4, 5000)
+    _cmp(res, ref)
+    y = Picard.transform(x[:, :777], res)
+    np.testing.assert_allclose(y, res.sources[:, :777], atol=1e-9)

@@ -24,6 +24,8 @@
 // both choices make every shared-memory access bank-conflict free.
 // =====================================================================================================
 #pragma once
+#include <type_traits>
+
 #include "pass.cuh"
 
 namespace picard {
@@ -172,40 +174,59 @@ rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, con
       }
     });
 
-    // acc[mb][nb][pp] <-> row 8 (MB warp + mb) + c, sample 2 (2 j + pp) + nb
+    // acc[mb][nb][pp] <-> row 8 (MB warp + mb) + c, sample 2 (2 j + pp) + nb.
+    // Two instantiations of the epilogue: interior tiles (every sample valid: no per-element bounds logic -- the epilogue is
+    // issue-bound, and every instruction saved shortens the time both warps of a scheduler spend off the DMMA pipe) and the
+    // one partial tile at the end of the shard.
+    auto epilogue = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-    for (int mb = 0; mb < MB; ++mb)
+      for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-      for (int pp = 0; pp < 2; ++pp)
+        for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-          double y = APPLY ? acc[mb][nb][pp] - brow[mb] : acc[mb][nb][pp];
-          const int64_t t = t0 + 4 * j + 2 * pp + nb;
-          const bool valid = !partial_tile || (t < p.t_local);
-          if (partial_tile && !valid) y = 0.0;
-          acc[mb][nb][pp] = y;
-          if (!APPLY) {
-            double f = 0.0, fd = 0.0, dsd = 0.0, dsl = 0.0;
-            density_eval<DENS, false, true>(y, p.dp, tab, f, fd, dsd, dsl);
-            if (valid) sl[mb] += dsl;  // loglik(0) != 0: padding columns must not reach L
-            if (WANT_SQ) sq[mb] = fma(y, y, sq[mb]);
+          for (int nb = 0; nb < 2; ++nb) {
+            double y = APPLY ? acc[mb][nb][pp] - brow[mb] : acc[mb][nb][pp];
+            bool valid = true;
+            if (!FULL) {
+              const int64_t t = t0 + 4 * j + 2 * pp + nb;
+              valid = t < p.t_local;
+              if (!valid) y = 0.0;
+            }
+            acc[mb][nb][pp] = y;
+            if (!APPLY) {
+              double f = 0.0, fd = 0.0, dsd = 0.0, dsl = 0.0;
+              if (FULL) {
+                density_eval<DENS, false, true>(y, p.dp, tab, f, fd, dsd, sl[mb]);
+              } else {
+                density_eval<DENS, false, true>(y, p.dp, tab, f, fd, dsd, dsl);
+                if (valid) sl[mb] += dsl;  // loglik(0) != 0: padding columns must not reach L
+              }
+              if (WANT_SQ) sq[mb] = fma(y, y, sq[mb]);
+            }
           }
-        }
-    if (p.out != nullptr) {  // Y' kept in HBM (LOSS: for the stored-Y gradient pass; APPLY: the result)
+      if (p.out != nullptr) {  // Y' kept in HBM (LOSS: for the stored-Y gradient pass; APPLY: the result)
 #pragma unroll
-      for (int mb = 0; mb < MB; ++mb) {
-        const int row = r0 + 8 * (MB * warp + mb) + c;
-        if (row < p.n_out) {
+        for (int mb = 0; mb < MB; ++mb) {
+          const int row = r0 + 8 * (MB * warp + mb) + c;
+          if (row < p.n_out) {
+            double* dst = p.out + (size_t)row * p.ld_out + t0 + 4 * j;
 #pragma unroll
-          for (int pp = 0; pp < 2; ++pp) {
-            const int64_t t = t0 + 4 * j + 2 * pp;
-            double* dst = p.out + (size_t)row * p.ld_out + t;
-            if (t + 1 < p.t_local) *reinterpret_cast<double2*>(dst) = make_double2(acc[mb][0][pp], acc[mb][1][pp]);
-            else if (t < p.t_local) dst[0] = acc[mb][0][pp];
+            for (int pp = 0; pp < 2; ++pp) {
+              if (FULL) {
+                *reinterpret_cast<double2*>(dst + 2 * pp) = make_double2(acc[mb][0][pp], acc[mb][1][pp]);
+              } else {
+                const int64_t t = t0 + 4 * j + 2 * pp;
+                if (t + 1 < p.t_local) *reinterpret_cast<double2*>(dst + 2 * pp) = make_double2(acc[mb][0][pp], acc[mb][1][pp]);
+                else if (t < p.t_local) dst[2 * pp] = acc[mb][0][pp];
+              }
+            }
           }
         }
       }
-    }
+    };
+    if (!partial_tile) epilogue(std::true_type{});
+    else epilogue(std::false_type{});
   }
 
   if (!APPLY) {
@@ -314,24 +335,36 @@ rb_grady_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, co
     ptx::mbar_wait(&bar[stage], parity);
 
     double psi[MB][2][2], psd[WANT_H ? MB : 1][2][2];
+    // interior tiles (every sample valid) take the instantiation without per-element bounds logic
+    auto own_elements = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-    for (int mb = 0; mb < MB; ++mb)
+      for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-      for (int nbp = 0; nbp < 2; ++nbp) {
-        const double2 v = *reinterpret_cast<const double2*>(yt + eoff[nbp] + mb * 8 * G::BT);
+        for (int nbp = 0; nbp < 2; ++nbp) {
+          const double2 v = *reinterpret_cast<const double2*>(yt + eoff[nbp] + mb * 8 * G::BT);
 #pragma unroll
-        for (int pp = 0; pp < 2; ++pp) {
-          double y = pp ? v.y : v.x;  // out-of-range columns / rows are zero-filled by the TMA unit
-          const int64_t t = t0 + 2 * (2 * j + nbp) + pp;
-          const bool valid = !partial_tile || (t < p.t_local);
-          if (HAS_BIAS) y = valid ? y - brow[mb] : 0.0;
-          double f = 0.0, fd = 0.0, dsd = 0.0, dsl = 0.0;
-          density_eval<DENS, true, false>(y, p.dp, tab, f, fd, dsd, dsl);
-          if (valid) sd[mb] += dsd;  // psi'(0) != 0: padding columns must not reach Sd
-          psi[mb][nbp][pp] = f;
-          if (WANT_H) { psd[mb][nbp][pp] = fd; sq[mb] = fma(y, y, sq[mb]); }
+          for (int pp = 0; pp < 2; ++pp) {
+            double y = pp ? v.y : v.x;  // out-of-range columns / rows are zero-filled by the TMA unit
+            bool valid = true;
+            if (!FULL) valid = (t0 + 2 * (2 * j + nbp) + pp) < p.t_local;
+            if (HAS_BIAS) y = valid ? y - brow[mb] : 0.0;
+            double f = 0.0, fd = 0.0, dsd = 0.0, dsl = 0.0;
+            if (FULL) {
+              density_eval<DENS, true, false>(y, p.dp, tab, f, fd, sd[mb], dsl);
+            } else {
+              density_eval<DENS, true, false>(y, p.dp, tab, f, fd, dsd, dsl);
+              if (valid) sd[mb] += dsd;  // psi'(0) != 0: padding columns must not reach Sd
+            }
+            psi[mb][nbp][pp] = f;
+            if (WANT_H) { psd[mb][nbp][pp] = fd; sq[mb] = fma(y, y, sq[mb]); }
+          }
         }
-      }
+    };
+    // measured: a win at NP = 256 (8.44 -> 8.13 ms), a loss at NP = 128 (11.39 -> 11.60 ms: the second copy of the unrolled
+    // density code costs more than the bounds logic it removes), so the specialisation is compiled for NP != 128 only
+    if (NP != 128 && !partial_tile) own_elements(std::true_type{});
+    else own_elements(std::false_type{});
 #pragma unroll
     for (int nbp = 0; nbp < 2; ++nbp)
 #pragma unroll

@@ -83,6 +83,17 @@ picard_comm* comm_create(const char id[PICARD_UNIQUE_ID_BYTES], int rank, int nr
   c->rank = rank; c->nranks = nranks; c->device = device;
   int rc = api().comm_init_rank(&c->nccl, nranks, u, rank);
   if (rc != 0) { delete c; nccl_check(rc, "ncclCommInitRank"); }
+  // first collective on a fresh communicator sets up channels / NVLS buffers (tens of ms): do it here, not inside the first fit
+  if (nranks > 1) {
+    double* tmp = nullptr;
+    if (cudaMalloc(&tmp, sizeof(double) * 1024) == cudaSuccess) {
+      cudaMemset(tmp, 0, sizeof(double) * 1024);
+      for (size_t cnt : {(size_t)1, (size_t)256, (size_t)1024})
+        api().all_reduce(tmp, tmp, cnt, kNcclFloat64, kNcclSum, c->nccl, 0);
+      cudaStreamSynchronize(0);
+      cudaFree(tmp);
+    }
+  }
   return c;
 }
 void comm_destroy(picard_comm* c) {

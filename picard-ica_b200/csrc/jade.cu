@@ -226,20 +226,42 @@ __global__ void __launch_bounds__(1024) jade_sweep_kernel(double* __restrict__ M
         }
         // ---- M' <- G^T M' G for every matrix: columns p, q then rows p, q (thread m <-> matrix m: coalesced)
         if (s_cs[2] != 0.0) {
+          // batches of 8 independent element pairs: 16 loads in flight per thread before the first dependent store (a plain
+          // load-compute-store loop serialises on L2 latency because the stores may alias the next loads)
           for (int m = tid; m < n_pairs; m += nt) {
-            for (int k = 0; k < n; ++k) {
-              double* ap = Mr + ((size_t)k * n + p) * m_pad + m;
-              double* aq = Mr + ((size_t)k * n + q) * m_pad + m;
-              const double x = *ap, y = *aq;
-              *ap = cc * x - ss * y;
-              *aq = ss * x + cc * y;
+            for (int k0 = 0; k0 < n; k0 += 8) {
+              double xv[8], yv[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u;
+                xv[u] = k < n ? Mr[((size_t)k * n + p) * m_pad + m] : 0.0;
+                yv[u] = k < n ? Mr[((size_t)k * n + q) * m_pad + m] : 0.0;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u;
+                if (k < n) {
+                  Mr[((size_t)k * n + p) * m_pad + m] = cc * xv[u] - ss * yv[u];
+                  Mr[((size_t)k * n + q) * m_pad + m] = ss * xv[u] + cc * yv[u];
+                }
+              }
             }
-            for (int k = 0; k < n; ++k) {
-              double* ap = Mr + ((size_t)p * n + k) * m_pad + m;
-              double* aq = Mr + ((size_t)q * n + k) * m_pad + m;
-              const double x = *ap, y = *aq;
-              *ap = cc * x - ss * y;
-              *aq = ss * x + cc * y;
+            for (int k0 = 0; k0 < n; k0 += 8) {
+              double xv[8], yv[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u;
+                xv[u] = k < n ? Mr[((size_t)p * n + k) * m_pad + m] : 0.0;
+                yv[u] = k < n ? Mr[((size_t)q * n + k) * m_pad + m] : 0.0;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u;
+                if (k < n) {
+                  Mr[((size_t)p * n + k) * m_pad + m] = cc * xv[u] - ss * yv[u];
+                  Mr[((size_t)q * n + k) * m_pad + m] = ss * xv[u] + cc * yv[u];
+                }
+              }
             }
           }
         }

@@ -330,8 +330,8 @@ def _main(out):
         roof = {"bound": "tensor", "kernel": {"loss": "rb_loss_kernel (LOSS + Y store)", "grady": "rb_grady_kernel (stored-Y gradient)"}.get(name, f"pass_kernel<{name}>"), "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": ach / FP64_PEAK_TFLOPS,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture at c3 on one GPU
-                # (profiles/summary_r01c.txt), scaled to this rank's share of the samples; null for kernels not captured
-                "traffic": {"loss": 20.437e9, "grady": 10.246e9}.get(name, None) and {"loss": 20.437e9, "grady": 10.246e9}[name] * (t_local / 1e7) * (n / 128.0)
+                # (profiles/summary_r01f.txt), scaled to this rank's share of the samples; null for kernels not captured
+                "traffic": {"loss": 20.436e9, "grady": 10.248e9}.get(name, None) and {"loss": 20.436e9, "grady": 10.248e9}[name] * (t_local / 1e7) * (n / 128.0)
                 if (n == 128) else None,
                 "algorithmic_bytes": (16.0 if name == "loss" else 8.0) * n * t_local, "avg_launch_ms": avg_ms, "launches": cnt,
                 "flops_per_launch": flops, "peak_source": "FP64 DMMA m8n8k4 microbenchmark measured by us "

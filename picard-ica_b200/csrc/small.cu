@@ -319,7 +319,6 @@ __global__ void negate_kernel(const double* G, double* D, int64_t count, CoreSca
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) D[e] = -G[e];
   if (blockIdx.x == 0 && threadIdx.x == 0) { sc->mem_len = 0; sc->mem_head = 0; sc->norm_d = sc->gradient_norm; }
 }
-__global__ void clear_memory_kernel(CoreScalars* sc) { sc->mem_len = 0; sc->mem_head = 0; }
 __global__ void scale_kernel(const double* A, double* B, int64_t count, double alpha) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) B[e] = A[e] * alpha;
 }
@@ -976,12 +975,6 @@ int matmul(const double* A, const double* B, double* C, int n, bool trans_b, dou
   LAUNCH_CHECK();
   return 1;
 }
-int matmul_rect(const double* A, const double* B, double* C, int m, int k, int n, cudaStream_t st) {
-  dim3 grid((n + 31) / 32, (m + 31) / 32);
-  matmul_kernel<false><<<grid, 256, 0, st>>>(A, B, C, m, k, n, 1.0, 0);
-  LAUNCH_CHECK();
-  return 1;
-}
 int set_identity(double* A, int n, cudaStream_t st) {
   identity_kernel<<<ew_blocks((int64_t)n * n), 256, 0, st>>>(A, n);
   LAUNCH_CHECK();
@@ -1021,11 +1014,6 @@ int accept_step(const CoreDims& d, const double* D, double alpha, double* S_prev
 }
 int negate_into(const double* G, double* D, int64_t count, CoreScalars* sc, cudaStream_t st) {
   negate_kernel<<<ew_blocks(count), 256, 0, st>>>(G, D, count, sc);
-  LAUNCH_CHECK();
-  return 1;
-}
-int clear_memory(CoreScalars* sc, cudaStream_t st) {
-  clear_memory_kernel<<<1, 1, 0, st>>>(sc);
   LAUNCH_CHECK();
   return 1;
 }

@@ -38,8 +38,6 @@ namespace small {
 // ---- generic helpers (each returns the number of kernels launched) ------------------------------------
 // C = alpha * A * op(B) (+ I if add_identity) ; all n x n, ld = n.  trans_b: use B^T.
 int matmul(const double* A, const double* B, double* C, int n, bool trans_b, double alpha, bool add_identity, cudaStream_t st);
-// rectangular: C (m x n) = A (m x k) * B (k x n), row-major, dense leading dimensions
-int matmul_rect(const double* A, const double* B, double* C, int m, int k, int n, cudaStream_t st);
 int set_identity(double* A, int n, cudaStream_t st);
 int copy_scaled(const double* A, double* B, int64_t count, double alpha, cudaStream_t st);  // B = alpha * A
 int eye_plus_scaled(const double* D, double alpha, double* M, int n, cudaStream_t st);      // M = I + alpha * D (core.rs:121)
@@ -70,7 +68,6 @@ int loss_from_moments(const CoreDims& d, const double* mom, const double* signs,
 int accept_step(const CoreDims& d, const double* D, double alpha, double* S_prev, const double* W, double* C, int update_c,
                 CoreScalars* sc, cudaStream_t st);
 int negate_into(const double* G, double* D, int64_t count, CoreScalars* sc, cudaStream_t st);  // fallback direction -G
-int clear_memory(CoreScalars* sc, cudaStream_t st);
 
 // ---- matrix_exp (math.rs:38-74): out = expm(alpha * D). norm_d = max|D| known to the host.
 struct ExpmWork { double* As; double* term0; double* term1; double* res0; double* res1; double* slots; };  // n^2 each; slots: EXPM_SLOTS

@@ -29,9 +29,19 @@
 namespace picard {
 namespace dmath {
 
-constexpr int EXP_TAB_N = 256;  // doubles
-constexpr int LOG_TAB_N = 256;  // doubles: 128 pairs {1/v0, -log(1/v0)}
-constexpr int TAB_DOUBLES = EXP_TAB_N + LOG_TAB_N;
+// Two table sets.  SMALL (4 KB) for the kernels that keep W in shared memory; BIG (80 KB) for the row-block kernels, whose
+// shared memory only holds the TMA stages: finer tables shorten the polynomials (exp 9 -> 8, log 7 -> 4 FP64 instructions).
+template <bool BIG>
+struct Tab {
+  static constexpr int EXP_BITS = BIG ? 11 : 8;
+  static constexpr int LOG_BITS = BIG ? 12 : 7;
+  static constexpr int EXP_N = 1 << EXP_BITS;          // doubles
+  static constexpr int LOG_N = 2 << LOG_BITS;          // doubles: pairs {1/v0, -log(1/v0)}
+  static constexpr int DOUBLES = EXP_N + LOG_N;
+};
+constexpr int EXP_TAB_N = Tab<false>::EXP_N;
+constexpr int LOG_TAB_N = Tab<false>::LOG_N;
+constexpr int TAB_DOUBLES = Tab<false>::DOUBLES;
 
 PICARD_HD int lo32(double t) {
 #ifdef __CUDA_ARCH__
@@ -80,30 +90,39 @@ PICARD_HD double rcp_nr(double d) {
   return r;
 }
 
-// exp(x) for x in [-700, 700] (callers clamp): x = n ln2/256 + r, |r| <= ln2/512; exp(r) - 1 by a degree-4 series
-// (truncation r^5/120 <= 4e-17); e = T[n & 255] (1 + q) 2^(n >> 8).  T = 2^(j/256) in shared memory.
+// exp(x) for x in [-700, 700] (callers clamp): x = n ln2/N + r, N = 2^EXP_BITS, |r| <= ln2/(2N); exp(r) - 1 by a series of
+// degree 4 (N = 256: r^5/120 <= 4e-17) or 3 (N = 2048: r^4/24 <= 4e-17); e = T[n mod N] (1 + q) 2^(n div N).
+template <bool BIG>
 PICARD_HD double exp_tab(double x, const double* __restrict__ T) {
-  const double C = 369.32993046757462709;  // 256 / ln 2
-  const double LHI = 6.93147180369123816490e-01 / 256.0, LLO = 1.90821492927058770002e-10 / 256.0;  // ln2/256 split; LHI has 32 trailing zero bits
+  constexpr int BITS = Tab<BIG>::EXP_BITS, N = 1 << BITS;
+  const double C = 1.4426950408889634074 * N;  // N / ln 2
+  const double LHI = 6.93147180369123816490e-01 / N, LLO = 1.90821492927058770002e-10 / N;  // ln2/N split; LHI has 32 trailing zero bits
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rint() by add/sub, the integer lands in the low word
   const double t = fma(x, C, MAGIC);
   const double kd = t - MAGIC;
   const int n = lo32(t);
   double r = fma(kd, -LHI, x);
   r = fma(kd, -LLO, r);
-  double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
-  p = fma(p, r, 0.5);
+  double p;
+  if (BIG) {
+    p = fma(r, 1.0 / 6.0, 0.5);
+  } else {
+    p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+  }
   p = fma(p, r, 1.0);
   const double q = p * r;
-  const double tj = T[n & (EXP_TAB_N - 1)];
-  return add_exponent(fma(tj, q, tj), n >> 8);
+  const double tj = T[n & (N - 1)];
+  return add_exponent(fma(tj, q, tj), n >> BITS);
 }
 
-// log(v) for v in [1, 2]: i = top 7 mantissa bits, v0 = 1 + (i + 1/2)/128, u = v/v0 - 1 (|u| <= 2^-8),
-// log v = -log(1/v0) + (u - u^2/2 + u^3/3 - u^4/4 + u^5/5)   (truncation u^6/6 <= 6e-16 absolute).
+// log(v) for v in [1, 2]: i = top LOG_BITS mantissa bits, v0 = 1 + (i + 1/2)/2^LOG_BITS, u = v/v0 - 1 (|u| <= 2^-(LOG_BITS+1)),
+// log v = -log(1/v0) + log1p(u) with the series to u^5 (128 entries: truncation u^6/6 <= 6e-16) or u^3 (4096 entries: u^4/4 <= 6e-17).
+template <bool BIG>
 PICARD_HD double log_1_2(double v, const double* __restrict__ LT) {
-  int i = (hi32(v) - 0x3FF00000) >> 13;
-  i = i < 127 ? i : 127;  // v == 2.0 exactly
+  constexpr int BITS = Tab<BIG>::LOG_BITS, NI = 1 << BITS;
+  int i = (hi32(v) - 0x3FF00000) >> (20 - BITS);
+  i = i < NI - 1 ? i : NI - 1;  // v == 2.0 exactly
 #ifdef __CUDA_ARCH__
   const double2 rl = reinterpret_cast<const double2*>(LT)[i];
   const double r0 = rl.x, l0 = rl.y;
@@ -111,6 +130,11 @@ PICARD_HD double log_1_2(double v, const double* __restrict__ LT) {
   const double r0 = LT[2 * i], l0 = LT[2 * i + 1];
 #endif
   const double u = fma(v, r0, -1.0);
+  if (BIG) {  // u - u^2/2 + u^3/3 = u (1 - u (1/2 - u/3))
+    double p = fma(u, -1.0 / 3.0, 0.5);
+    p = fma(-u, p, 1.0);
+    return fma(p, u, l0);
+  }
   double p = fma(u, 0.2, -0.25);
   p = fma(p, u, 1.0 / 3.0);
   p = fma(p, u, -0.5);
@@ -141,14 +165,14 @@ inline DensParams make_dens_params(int dens, double alpha) {
 //   cube (density.rs:122-130): psi = y^3, psi' = 3 y^2, loglik = y^4 / 4
 //   linear (internal): psi = y, psi' = 1, loglik = y^2 / 2   (covariance SYRK of the whitening step)
 // NEED_PSI: psi / psi' wanted (psi' is added to sd);  NEED_LL: log-likelihood wanted (added to sl).
-// tab: [exp table 256][log table 256] (shared memory on the device).
-template <int DENS, bool NEED_PSI, bool NEED_LL>
+// tab: [exp table][log table] of the SMALL or BIG set (shared memory on the device).
+template <int DENS, bool NEED_PSI, bool NEED_LL, bool BIG = false>
 PICARD_HD void density_eval(double y, const DensParams& dp, const double* __restrict__ tab, double& psi, double& psid, double& sd,
                             double& sl) {
   if (DENS == DENS_TANH) {
     const double ay = fabs(y);
     const double x = dmath::clamp_hi(ay, dp.hi_limit) * dp.xscale;
-    const double e = dmath::exp_tab(x, tab);
+    const double e = dmath::exp_tab<BIG>(x, tab);
     const double v = 1.0 + e;
     if (NEED_PSI) {
       const double r = dmath::rcp_nr(v);
@@ -159,12 +183,12 @@ PICARD_HD void density_eval(double y, const DensParams& dp, const double* __rest
     }
     if (NEED_LL) {
       sl += ay;
-      sl = fma(dmath::log_1_2(v, tab + dmath::EXP_TAB_N), dp.inv_alpha, sl);
+      sl = fma(dmath::log_1_2<BIG>(v, tab + dmath::Tab<BIG>::EXP_N), dp.inv_alpha, sl);
     }
   } else if (DENS == DENS_EXP) {
     const double y2 = y * y;
     const double x = dmath::clamp_hi(y2, dp.hi_limit) * dp.xscale;
-    const double k = dmath::exp_tab(x, tab);
+    const double k = dmath::exp_tab<BIG>(x, tab);
     if (NEED_PSI) {
       psi = y * k;
       psid = fma(-dp.alpha, y2, 1.0) * k;

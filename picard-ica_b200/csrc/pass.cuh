@@ -76,6 +76,19 @@ struct PassParams {
 // lookup tables of density.cuh in global memory (one copy per translation unit); staged into shared memory per CTA
 static __device__ const double g_exp_tab[dmath::EXP_TAB_N] = PICARD_EXP_TAB_INIT;
 static __device__ const double g_log_tab[dmath::LOG_TAB_N] = PICARD_LOG_TAB_INIT;
+static __device__ const double g_exp_tab_big[dmath::Tab<true>::EXP_N] = PICARD_EXP_TAB_BIG_INIT;
+static __device__ const double g_log_tab_big[dmath::Tab<true>::LOG_N] = PICARD_LOG_TAB_BIG_INIT;
+
+// stage a table set into shared memory ([exp][log]); the log part only when a log-likelihood is evaluated
+template <bool BIG>
+__device__ __forceinline__ void load_density_tables(double* tab, bool need_log, int tid, int nthreads) {
+  using TB = dmath::Tab<BIG>;
+  const double* ge = BIG ? g_exp_tab_big : g_exp_tab;
+  const double* gl = BIG ? g_log_tab_big : g_log_tab;
+  for (int i = tid; i < TB::EXP_N; i += nthreads) tab[i] = ge[i];
+  if (need_log)
+    for (int i = tid; i < TB::LOG_N; i += nthreads) tab[TB::EXP_N + i] = gl[i];
+}
 
 namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

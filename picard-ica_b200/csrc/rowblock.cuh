@@ -30,6 +30,18 @@
 
 namespace picard {
 
+#ifdef PICARD_RB_TRACE
+// Debug build only (profiles/rb_trace.sh): clock64() at the phase boundaries of every warp of CTA 0 for the first tiles.
+constexpr int RB_TRACE_TILES = 96;
+static __device__ long long g_rb_trace[16 * RB_TRACE_TILES * 8];
+#define RB_TRACE(slot)                                                                                         \
+  do {                                                                                                         \
+    if (blockIdx.x == 0 && lane == 0 && it < RB_TRACE_TILES) g_rb_trace[(warp * RB_TRACE_TILES + (int)it) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define RB_TRACE(slot) do { } while (0)
+#endif
+
 __host__ __device__ inline int rb_partial_size(int rp, int np, bool want_g, bool want_h) {
   return (want_g ? rp * np : 0) + (want_h ? rp * np : 0) + 3 * rp;
 }
@@ -83,7 +95,8 @@ struct RbLossGeom {
   static constexpr int BT = 16;
   static constexpr int STAGES = KP == 256 ? 4 : 6;
   static constexpr int MIN_BLOCKS = KP == 64 ? 2 : 1;  // KP = 64: 16 A-fragment doubles per thread, two CTAs per SM
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * KP * BT * 8 + (size_t)dmath::TAB_DOUBLES * 8 + 128;
+  static constexpr bool BIG_TAB = KP >= 128;           // 80 KB of density tables next to the stages (one CTA per SM anyway)
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * KP * BT * 8 + (size_t)dmath::Tab<BIG_TAB>::DOUBLES * 8 + 128;
 };
 
 template <int KP, int DENS, int MODE, bool WANT_SQ>
@@ -95,8 +108,9 @@ rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, con
   constexpr int MB = G::MB, KS = G::KS;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double* xs = reinterpret_cast<double*>(smem_raw);
+  constexpr bool BIG = G::BIG_TAB;
   double* tab = xs + G::STAGES * KP * G::BT;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(tab + dmath::TAB_DOUBLES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tab + dmath::Tab<BIG>::DOUBLES);
   int* cnt = reinterpret_cast<int*>(bar + G::STAGES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -104,8 +118,7 @@ rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, con
   const int rb = blockIdx.x % nrb, tg = blockIdx.x / nrb, n_tg = gridDim.x / nrb;
   const int r0 = rb * G::RP;
 
-  if (NEED_TAB)
-    for (int i = tid; i < dmath::EXP_TAB_N; i += G::NTHREADS) { tab[i] = g_exp_tab[i]; tab[dmath::EXP_TAB_N + i] = g_log_tab[i]; }
+  if (NEED_TAB) load_density_tables<BIG>(tab, DENS == DENS_TANH, tid, G::NTHREADS);
   if (tid == 0) {
     ptx::prefetch_tmap(&tmap);
     for (int s = 0; s < G::STAGES; ++s) { ptx::mbar_init(&bar[s], 1); cnt[s] = 0; }
@@ -150,7 +163,9 @@ rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, con
     const int64_t t0 = (tile0 + it * tstride) * G::BT;
     const bool partial_tile = (t0 + G::BT > p.t_local);
     const double* xst = xs + stage * KP * G::BT;
+    RB_TRACE(0);
     ptx::mbar_wait(&bar[stage], parity);
+    RB_TRACE(1);
 
     double acc[MB][2][2];
 #pragma unroll
@@ -174,6 +189,7 @@ rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, con
       }
     });
 
+    RB_TRACE(2);
     // acc[mb][nb][pp] <-> row 8 (MB warp + mb) + c, sample 2 (2 j + pp) + nb.
     // Two instantiations of the epilogue: interior tiles (every sample valid: no per-element bounds logic -- the epilogue is
     // issue-bound, and every instruction saved shortens the time both warps of a scheduler spend off the DMMA pipe) and the
@@ -197,9 +213,9 @@ rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, con
             if (!APPLY) {
               double f = 0.0, fd = 0.0, dsd = 0.0, dsl = 0.0;
               if (FULL) {
-                density_eval<DENS, false, true>(y, p.dp, tab, f, fd, dsd, sl[mb]);
+                density_eval<DENS, false, true, BIG>(y, p.dp, tab, f, fd, dsd, sl[mb]);
               } else {
-                density_eval<DENS, false, true>(y, p.dp, tab, f, fd, dsd, dsl);
+                density_eval<DENS, false, true, BIG>(y, p.dp, tab, f, fd, dsd, dsl);
                 if (valid) sl[mb] += dsl;  // loglik(0) != 0: padding columns must not reach L
               }
               if (WANT_SQ) sq[mb] = fma(y, y, sq[mb]);
@@ -227,6 +243,7 @@ rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, con
     };
     if (!partial_tile) epilogue(std::true_type{});
     else epilogue(std::false_type{});
+    RB_TRACE(3);
   }
 
   if (!APPLY) {
@@ -259,7 +276,9 @@ struct RbGradYGeom {
   static constexpr int BT = 16;
   static constexpr int STAGES = NP == 256 ? 4 : 6;
   static constexpr int MIN_BLOCKS = NP >= 128 ? 1 : (NP == 64 ? 2 : (NP == 32 ? 4 : 8));
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * NP * BT * 8 + (size_t)dmath::TAB_DOUBLES * 8 + (size_t)NP * 8 + 128;
+  static constexpr bool BIG_TAB = NP >= 128;  // only the exp part (16 KB) is staged: no log-likelihood in this kernel
+  static constexpr size_t TAB_BYTES = (size_t)(BIG_TAB ? dmath::Tab<true>::EXP_N : dmath::TAB_DOUBLES) * 8;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * NP * BT * 8 + TAB_BYTES + (size_t)NP * 8 + 128;
   static_assert(MB * NBW * (WANT_H ? 2 : 1) <= 32, "accumulators exceed 128 registers per thread");
 };
 
@@ -271,8 +290,9 @@ rb_grady_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, co
   constexpr bool NEED_TAB = (DENS == DENS_TANH || DENS == DENS_EXP);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double* ysm = reinterpret_cast<double*>(smem_raw);
+  constexpr bool BIG = G::BIG_TAB;
   double* tab = ysm + G::STAGES * NP * G::BT;
-  double* bs = tab + dmath::TAB_DOUBLES;
+  double* bs = tab + G::TAB_BYTES / 8;
   uint64_t* bar = reinterpret_cast<uint64_t*>(bs + NP);
   int* cnt = reinterpret_cast<int*>(bar + G::STAGES);
 
@@ -283,8 +303,7 @@ rb_grady_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, co
   const int row0 = rb * G::RP + 8 * MB * rg;  // first row of this warp (multiple of 8)
   const int col0 = ch * NBW * 8;              // first column of this warp
 
-  if (NEED_TAB)
-    for (int i = tid; i < dmath::EXP_TAB_N; i += G::NTHREADS) { tab[i] = g_exp_tab[i]; tab[dmath::EXP_TAB_N + i] = g_log_tab[i]; }
+  if (NEED_TAB) load_density_tables<BIG>(tab, false, tid, G::NTHREADS);
   if (HAS_BIAS)
     for (int i = tid; i < NP; i += G::NTHREADS) bs[i] = (p.bias != nullptr && i < p.n_out) ? p.bias[i] : 0.0;
   if (tid == 0) {
@@ -351,9 +370,9 @@ rb_grady_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, co
             if (HAS_BIAS) y = valid ? y - brow[mb] : 0.0;
             double f = 0.0, fd = 0.0, dsd = 0.0, dsl = 0.0;
             if (FULL) {
-              density_eval<DENS, true, false>(y, p.dp, tab, f, fd, sd[mb], dsl);
+              density_eval<DENS, true, false, BIG>(y, p.dp, tab, f, fd, sd[mb], dsl);
             } else {
-              density_eval<DENS, true, false>(y, p.dp, tab, f, fd, dsd, dsl);
+              density_eval<DENS, true, false, BIG>(y, p.dp, tab, f, fd, dsd, dsl);
               if (valid) sd[mb] += dsd;  // psi'(0) != 0: padding columns must not reach Sd
             }
             psi[mb][nbp][pp] = f;

@@ -1,5 +1,5 @@
 """Per-pass timing of the fused kernel on device-resident synthetic data (picard_eval_moments_device).
-Usage: python profiles/pass_bench.py [N] [T] [repeats] [density kind]   -> one JSON line per pass mode."""
+Usage: python profiles/pass_bench.py [N] [T] [repeats] [density kind] [pass,pass,...]   -> one JSON line per pass mode."""
 import ctypes as C
 import json
 import os
@@ -17,6 +17,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 t = int(float(sys.argv[2])) if len(sys.argv) > 2 else 10_000_000
 rep = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 kind = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+only = sys.argv[5].split(",") if len(sys.argv) > 5 else None  # e.g. loss,gradY
 lib = _ffi.lib()
 ld = (t + 15) // 16 * 16
 x = torch.empty((n, ld), dtype=torch.float64, device="cuda")
@@ -26,6 +27,8 @@ w = np.ascontiguousarray(_data.orthogonal(n, 43))
 peak = 37.19
 for mode, name, fl in [(0, "fused", 4.0), (1, "grad", 4.0), (2, "loss", 2.0), (3, "loss+store,gradY", 4.0), (4, "gradY", 2.0),
                        (0, "fused+H", 6.0), (1, "grad+H", 6.0), (4, "gradY+H", 4.0)]:
+    if only and name not in only:
+        continue
     want_h = name.endswith("+H")
     ms = C.c_double()
     err = C.create_string_buffer(512)

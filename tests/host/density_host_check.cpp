@@ -9,12 +9,17 @@
 
 using namespace picard;
 
-static const double EXP_TAB[] = PICARD_EXP_TAB_INIT;
-static const double LOG_TAB[] = PICARD_LOG_TAB_INIT;
+static const double EXP_TAB_S[] = PICARD_EXP_TAB_INIT;
+static const double LOG_TAB_S[] = PICARD_LOG_TAB_INIT;
+static const double EXP_TAB_B[] = PICARD_EXP_TAB_BIG_INIT;
+static const double LOG_TAB_B[] = PICARD_LOG_TAB_BIG_INIT;
 
-int main() {
-  double tab[dmath::TAB_DOUBLES];
-  for (int i = 0; i < 256; ++i) { tab[i] = EXP_TAB[i]; tab[256 + i] = LOG_TAB[i]; }
+template <bool BIG>
+static int run() {
+  using TB = dmath::Tab<BIG>;
+  static double tab[TB::DOUBLES];
+  for (int i = 0; i < TB::EXP_N; ++i) tab[i] = BIG ? EXP_TAB_B[i] : EXP_TAB_S[i];
+  for (int i = 0; i < TB::LOG_N; ++i) tab[TB::EXP_N + i] = BIG ? LOG_TAB_B[i] : LOG_TAB_S[i];
   double max_exp = 0, max_log = 0, max_psi = 0, max_psid_abs = 0, max_ll = 0, max_k = 0;
   unsigned long long s = 88172645463325252ull;
   auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (double)(s >> 11) / 9007199254740992.0; };
@@ -22,7 +27,7 @@ int main() {
   for (int it = 0; it < n; ++it) {
     // exp on [-700, 0.5]
     double x = (it % 3 == 0) ? -700.0 * rnd() : ((it % 3 == 1) ? -40.0 * rnd() : -2.0 * rnd() + 0.5 * rnd());
-    double e = dmath::exp_tab(x, tab);
+    double e = dmath::exp_tab<BIG>(x, tab);
     long double er = expl((long double)x);
     double rel = (double)fabsl(((long double)e - er) / er);
     if (rel > max_exp) max_exp = rel;
@@ -30,7 +35,7 @@ int main() {
     double v = 1.0 + rnd();
     if (it == 0) v = 1.0;
     if (it == 1) v = 2.0;
-    double l = dmath::log_1_2(v, tab + 256);
+    double l = dmath::log_1_2<BIG>(v, tab + TB::EXP_N);
     long double lr = logl((long double)v);
     double ab = (double)fabsl((long double)l - lr);
     if (ab > max_log) max_log = ab;
@@ -45,7 +50,7 @@ int main() {
         if (it == 2) y = 1e300;
         double psi = 0, psid = 0, sd = 0, sl = 0;
         if (dens == 0) {
-          density_eval<DENS_TANH, true, true>(y, dp, tab, psi, psid, sd, sl);
+          density_eval<DENS_TANH, true, true, BIG>(y, dp, tab, psi, psid, sd, sl);
           long double a = alpha, yy = y;
           long double ps = tanhl(a * yy), pd = a * (1 - ps * ps), ll = fabsl(yy) + logl(1 + expl(-2 * a * fabsl(yy))) / a;
           double r1 = (double)fabsl(((long double)psi - ps));  // absolute: (1 - e) cancels for tiny |y|, like any exp-based tanh
@@ -56,7 +61,7 @@ int main() {
           if (r3 > max_ll) max_ll = r3;
         } else {
           if (fabs(y) > 100) continue;
-          density_eval<DENS_EXP, true, true>(y, dp, tab, psi, psid, sd, sl);
+          density_eval<DENS_EXP, true, true, BIG>(y, dp, tab, psi, psid, sd, sl);
           long double a = alpha, yy = y;
           long double k = expl(-a * yy * yy / 2);
           double r1 = (double)fabsl((long double)psi - yy * k), r2 = (double)fabsl((long double)psid - (1 - a * yy * yy) * k);
@@ -67,7 +72,9 @@ int main() {
       }
     }
   }
-  printf("{\"exp_rel\": %.3e, \"log_abs\": %.3e, \"tanh_psi_abs\": %.3e, \"tanh_psid_abs\": %.3e, \"tanh_ll_rel\": %.3e, \"expdens_abs\": %.3e}\n",
-         max_exp, max_log, max_psi, max_psid_abs, max_ll, max_k);
+  printf("{\"set\": \"%s\", \"exp_rel\": %.3e, \"log_abs\": %.3e, \"tanh_psi_abs\": %.3e, \"tanh_psid_abs\": %.3e, \"tanh_ll_rel\": %.3e, \"expdens_abs\": %.3e}\n",
+         BIG ? "big" : "small", max_exp, max_log, max_psi, max_psid_abs, max_ll, max_k);
   return 0;
 }
+
+int main() { return run<false>() | run<true>(); }

@@ -17,13 +17,16 @@ def test_density_polynomials_on_host(tmp_path):
     cuda_inc = "/usr/local/cuda/include"
     subprocess.run(["g++", "-O2", "-std=c++17", f"-I{cuda_inc}", os.path.join(ROOT, "tests", "host", "density_host_check.cpp"), "-o", exe],
                    check=True)
-    out = json.loads(subprocess.run([exe], check=True, capture_output=True, text=True).stdout)
-    assert out["exp_rel"] < 4e-16        # exp on [-700, 0.5], relative
-    assert out["log_abs"] < 1e-15        # log on [1, 2], absolute
-    assert out["tanh_psi_abs"] < 1e-15   # tanh(alpha y), absolute
-    assert out["tanh_psid_abs"] < 3e-15  # alpha (1 - tanh^2), absolute (alpha up to 2.5)
-    assert out["tanh_ll_rel"] < 1e-15    # |y| + log(1 + exp(-2 alpha |y|)) / alpha, relative
-    assert out["expdens_abs"] < 1e-15    # exp density: psi, psi', log-lik, absolute up to their polynomial prefactors
+    lines = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    outs = [json.loads(l) for l in lines]
+    assert sorted(o["set"] for o in outs) == ["big", "small"]  # both table sets (4 KB and 80 KB)
+    for out in outs:
+        assert out["exp_rel"] < 4e-16        # exp on [-700, 0.5], relative
+        assert out["log_abs"] < 1e-15        # log on [1, 2], absolute
+        assert out["tanh_psi_abs"] < 1e-15   # tanh(alpha y), absolute
+        assert out["tanh_psid_abs"] < 3e-15  # alpha (1 - tanh^2), absolute (alpha up to 2.5)
+        assert out["tanh_ll_rel"] < 1e-15    # |y| + log(1 + exp(-2 alpha |y|)) / alpha, relative
+        assert out["expdens_abs"] < 1e-15    # exp density: psi, psi', log-lik, absolute up to their polynomial prefactors
 
 
 def test_tables_are_reproducible():

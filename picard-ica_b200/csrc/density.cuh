@@ -4,11 +4,14 @@
 // additive; ncu on the pass kernel: DMMA sub-pipe % + FP64 pipe % = SM throughput %), so every FP64 instruction
 // spent here is taken from the contraction budget (4 N flop per element = 8 pipe-instructions at N = 128).
 // Everything below is therefore built to minimise FP64-pipe instructions, moving work to pipes that are idle:
-//   * exp: Cody-Waite reduction to |r| <= ln2/512 with a 256-entry table of 2^(j/256) in shared memory (LSU) and
-//     the exponent inserted by integer adds (ALU): 9 FP64 instructions instead of 18 for a table-free degree-12 series;
+//   * exp(s z) (s = -2 alpha, z = |y| for tanh; s = -alpha/2, z = y^2 for exp): one-fma reduction to |s r| <= ln2/512 (ln2/4096
+//     with the BIG tables), the scale s folded into the reduction constants and the series coefficients, a table of 2^(j/N)
+//     in shared memory (LSU), the exponent inserted by integer adds (ALU): 8 (7) FP64 instructions, scaling included,
+//     instead of 19 for a table-free degree-12 series;
 //   * log(1 + e), 1 + e in [1, 2]: 128-entry table {1/v0, -log(1/v0)} indexed by the top mantissa bits (ALU),
 //     u = fma(v, 1/v0, -1), |u| <= 2^-8, degree-5 series: 7 FP64 instructions instead of 22;
-//   * reciprocal seeds from the SFU (MUFU.RCP64H) + 2 Newton steps; |y| and sign transfers by integer ops;
+//   * quotients from an SFU seed (MUFU.RCP64H) and one second-order correction (5 FP64 instructions); |y| and sign
+//     transfers by integer ops;
 //   * range clamps by integer min on the high word; one e = exp(-2 alpha |y|) shared by tanh, 1 - tanh^2 and log-lik.
 // Accuracy: <= ~1e-15 relative per element (the parity bar on the sums G, h, loss is 1e-10; measured ~1e-13).
 // Everything is host-callable so the polynomials are checked on the CPU (tests/test_density_host.py).
@@ -77,8 +80,17 @@ PICARD_HD double rcp_seed(double d) {
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
   return r;
 #else
-  return (double)(1.0f / (float)d);
+  // host model of MUFU.RCP64H: only the high word of the operand is read, only the high word of the result is written
+  return make_double(hi32(1.0 / make_double(hi32(d), 0)), 0);
 #endif
+}
+// (a / d) for d in a benign range: seed r0 (2^-20), e = 1 - d r0, 1/d = r0 (1 + e + e^2 + O(e^3)), O(e^3) ~ 2^-60.
+PICARD_HD double div_seeded(double a, double d) {
+  const double r0 = rcp_seed(d);
+  const double e = fma(-d, r0, 1.0);
+  const double s = fma(e, e, e);
+  const double t0 = a * r0;
+  return fma(t0, s, t0);
 }
 // 1/d for d in a benign range (no zero/inf/denormal handling): seed + 2 Newton steps (2^-20 -> 2^-80).
 PICARD_HD double rcp_nr(double d) {
@@ -90,27 +102,39 @@ PICARD_HD double rcp_nr(double d) {
   return r;
 }
 
-// exp(x) for x in [-700, 700] (callers clamp): x = n ln2/N + r, N = 2^EXP_BITS, |r| <= ln2/(2N); exp(r) - 1 by a series of
-// degree 4 (N = 256: r^5/120 <= 4e-17) or 3 (N = 2048: r^4/24 <= 4e-17); e = T[n mod N] (1 + q) 2^(n div N).
+// Constants of one density, prepared on the host (make_dens_params below).
+struct DensParams {
+  double alpha, inv_alpha;
+  double xscale;   // s: tanh -2 alpha (exponent s |y|) ; exp -alpha / 2 (exponent s y^2)
+  int hi_limit;    // high word of the clamp on z = |y| (tanh) or y^2 (exp) that keeps s z >= -700
+  // exp(s z) with the scale folded into the range reduction and the series (index 0: SMALL tables, 1: BIG tables)
+  double ct[2];    // s N / ln 2
+  double nlr[2];   // -ln 2 / (s N)
+  double c1, c2, c3, c4;  // s, s^2/2, s^3/6, s^4/24
+};
+
+// exp(s z) for z >= 0, s < 0, s z >= -700 (callers clamp z): z = n L + r with L = ln2 / (s N), N = 2^EXP_BITS, |s r| <= ln2/(2N);
+// exp(s r) - 1 by a series in r with the powers of s folded into the coefficients, degree 4 (N = 256: (s r)^5/120 <= 4e-17) or
+// 3 (N = 2048: (s r)^4/24 <= 4e-17); result T[n mod N] (1 + q) 2^(n div N).  ONE fma for the reduction: the rounding of L
+// perturbs the exponent by |s z| 2^-53, a relative error |s z| 1.1e-16 of a result that is <= exp(-|s z|) -- the same order as
+// rounding the product s z itself (what a libm-based evaluation of exp(s * z) starts from).  7 FP64 instructions with the BIG
+// tables, 8 with the SMALL ones, the multiplication by s included.
 template <bool BIG>
-PICARD_HD double exp_tab(double x, const double* __restrict__ T) {
+PICARD_HD double exp_scaled(double z, const DensParams& dp, const double* __restrict__ T) {
   constexpr int BITS = Tab<BIG>::EXP_BITS, N = 1 << BITS;
-  const double C = 1.4426950408889634074 * N;  // N / ln 2
-  const double LHI = 6.93147180369123816490e-01 / N, LLO = 1.90821492927058770002e-10 / N;  // ln2/N split; LHI has 32 trailing zero bits
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rint() by add/sub, the integer lands in the low word
-  const double t = fma(x, C, MAGIC);
+  const double t = fma(z, dp.ct[BIG ? 1 : 0], MAGIC);
   const double kd = t - MAGIC;
   const int n = lo32(t);
-  double r = fma(kd, -LHI, x);
-  r = fma(kd, -LLO, r);
+  const double r = fma(kd, dp.nlr[BIG ? 1 : 0], z);
   double p;
   if (BIG) {
-    p = fma(r, 1.0 / 6.0, 0.5);
+    p = fma(r, dp.c3, dp.c2);
   } else {
-    p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
+    p = fma(r, dp.c4, dp.c3);
+    p = fma(p, r, dp.c2);
   }
-  p = fma(p, r, 1.0);
+  p = fma(p, r, dp.c1);
   const double q = p * r;
   const double tj = T[n & (N - 1)];
   return add_exponent(fma(tj, q, tj), n >> BITS);
@@ -143,19 +167,22 @@ PICARD_HD double log_1_2(double v, const double* __restrict__ LT) {
 }
 
 }  // namespace dmath
+using dmath::DensParams;
 
-// Constants of one density, prepared on the host.
-struct DensParams {
-  double alpha, inv_alpha;
-  double xscale;   // tanh: -2 alpha (x = xscale * |y|) ; exp: -alpha / 2 (x = xscale * y^2)
-  int hi_limit;    // high word of the clamp on |y| (tanh) or y^2 (exp) that keeps x >= -700
-};
 inline DensParams make_dens_params(int dens, double alpha) {
   DensParams d;
   d.alpha = alpha; d.inv_alpha = 1.0 / alpha;
-  d.xscale = dens == DENS_TANH ? -2.0 * alpha : -0.5 * alpha;
-  const double lim = 700.0 / std::fabs(d.xscale);
+  const double s = dens == DENS_TANH ? -2.0 * alpha : -0.5 * alpha;
+  d.xscale = s;
+  const double lim = 700.0 / std::fabs(s);
   d.hi_limit = dmath::hi32(lim);
+  const double ln2 = 6.93147180559945309417e-01;
+  for (int b = 0; b < 2; ++b) {
+    const double n = b ? (double)dmath::Tab<true>::EXP_N : (double)dmath::Tab<false>::EXP_N;
+    d.ct[b] = s * n / ln2;
+    d.nlr[b] = -ln2 / (s * n);
+  }
+  d.c1 = s; d.c2 = s * s / 2.0; d.c3 = s * s * s / 6.0; d.c4 = s * s * s * s / 24.0;
   return d;
 }
 
@@ -171,13 +198,11 @@ PICARD_HD void density_eval(double y, const DensParams& dp, const double* __rest
                             double& sl) {
   if (DENS == DENS_TANH) {
     const double ay = fabs(y);
-    const double x = dmath::clamp_hi(ay, dp.hi_limit) * dp.xscale;
-    const double e = dmath::exp_tab<BIG>(x, tab);
+    const double e = dmath::exp_scaled<BIG>(dmath::clamp_hi(ay, dp.hi_limit), dp, tab);  // exp(-2 alpha |y|)
     const double v = 1.0 + e;
     if (NEED_PSI) {
-      const double r = dmath::rcp_nr(v);
-      const double th = (1.0 - e) * r;            // tanh(alpha |y|)
-      psi = copysign(th, y * dp.alpha);           // tanh(alpha y): sign transfer on the ALU (alpha > 0 in practice)
+      const double th = dmath::div_seeded(1.0 - e, v);  // tanh(alpha |y|)
+      psi = copysign(th, y);                            // tanh(alpha y) (alpha > 0): sign transfer on the ALU
       psid = dp.alpha * fma(-th, th, 1.0);
       sd += psid;
     }
@@ -187,8 +212,7 @@ PICARD_HD void density_eval(double y, const DensParams& dp, const double* __rest
     }
   } else if (DENS == DENS_EXP) {
     const double y2 = y * y;
-    const double x = dmath::clamp_hi(y2, dp.hi_limit) * dp.xscale;
-    const double k = dmath::exp_tab<BIG>(x, tab);
+    const double k = dmath::exp_scaled<BIG>(dmath::clamp_hi(y2, dp.hi_limit), dp, tab);  // exp(-alpha y^2 / 2)
     if (NEED_PSI) {
       psi = y * k;
       psid = fma(-dp.alpha, y2, 1.0) * k;

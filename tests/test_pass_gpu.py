@@ -131,3 +131,35 @@ def test_large_values_saturate_cleanly():
     for k in ("gr", "sd", "sq", "lrow"):
         assert np.all(np.isfinite(got[k]))
         assert _data.rel_err(got[k], getattr(ref, k)) <= TOL
+
+
+_WS_SCRIPT = r"""
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import numpy as np
+import _data, _gpu
+from oracle import oracle as orc
+for n, t, kind, alpha in [(128, 2050, orc.TANH, 1.0), (100, 1500, orc.TANH, 1.0), (256, 1040, orc.EXP, 0.1), (200, 2001, orc.TANH, 1.0)]:
+    x = _data.whitened(n, t, seed=n)
+    w = _data.orthogonal(n, seed=n + 2) + 0.02 * np.random.default_rng(n).standard_normal((n, n))
+    ref = orc.eval_point(x, w, kind, alpha, ortho=False, extended=False)
+    for want_h in (True, False):
+        got = _gpu.eval_moments(x, w, kind, alpha, mode=3, want_h=want_h)   # LOSS + Y store (TMA store), then gradient from the stored Y
+        for k in ("gr", "sd", "lrow") + (("hr", "sq") if want_h else ()):
+            e = _data.rel_err(got[k], getattr(ref, k))
+            assert e <= 1e-10, (n, t, k, e)
+print("ok")
+"""
+
+
+def test_warp_specialised_loss_kernel_is_parity_green():
+    """rowblock_ws.cuh (PICARD_RB_WS=1, an opt-in experiment): same raw moments as the oracle, ragged last tile and N < KP included.
+    The switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PICARD_RB_WS="1")
+    r = subprocess.run([sys.executable, "-c", _WS_SCRIPT.format(root=root, tests=os.path.join(root, "tests"))], env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr

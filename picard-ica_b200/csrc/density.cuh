@@ -39,7 +39,7 @@ struct Tab {
   static constexpr int EXP_BITS = BIG ? 11 : 8;
   static constexpr int LOG_BITS = BIG ? 12 : 7;
   static constexpr int EXP_N = 1 << EXP_BITS;          // doubles
-  static constexpr int LOG_N = 2 << LOG_BITS;          // doubles: pairs {1/v0, -log(1/v0)}
+  static constexpr int LOG_N = 2 * ((1 << LOG_BITS) + 1);  // doubles: pairs {1/v0, -log(1/v0)}, one extra pair for v == 2.0
   static constexpr int DOUBLES = EXP_N + LOG_N;
 };
 constexpr int EXP_TAB_N = Tab<false>::EXP_N;
@@ -144,9 +144,8 @@ PICARD_HD double exp_scaled(double z, const DensParams& dp, const double* __rest
 // log v = -log(1/v0) + log1p(u) with the series to u^5 (128 entries: truncation u^6/6 <= 6e-16) or u^3 (4096 entries: u^4/4 <= 6e-17).
 template <bool BIG>
 PICARD_HD double log_1_2(double v, const double* __restrict__ LT) {
-  constexpr int BITS = Tab<BIG>::LOG_BITS, NI = 1 << BITS;
-  int i = (hi32(v) - 0x3FF00000) >> (20 - BITS);
-  i = i < NI - 1 ? i : NI - 1;  // v == 2.0 exactly
+  constexpr int BITS = Tab<BIG>::LOG_BITS;
+  const int i = (hi32(v) - 0x3FF00000) >> (20 - BITS);  // v == 2.0 exactly (y == 0) lands on the extra entry NI
 #ifdef __CUDA_ARCH__
   const double2 rl = reinterpret_cast<const double2*>(LT)[i];
   const double r0 = rl.x, l0 = rl.y;

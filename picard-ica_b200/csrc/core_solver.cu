@@ -9,6 +9,7 @@
 //   * the per-row log-likelihood sums L_i are kept with each point, so the loss under new signs
 //     (core.rs:317-329) and the initial loss (core.rs:185) need no extra pass.
 #include "engine.cuh"
+#include "i8_loss.cuh"
 
 #include <chrono>
 #include <map>
@@ -186,8 +187,14 @@ void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
   const bool store = store_y && mode == PASS_LOSS && ybuf_.p != nullptr;
   L.d_out = store ? ybuf_.p : nullptr; L.ld_out = store ? ldx_ : 0;
   if (mode == PASS_LOSS) ybuf_valid_ = store;
+  const bool use_i8 = i8_enabled() && mode == PASS_LOSS && pass_padded_size(dims_.n) == 128;
+  if (use_i8 && !xs8_.p) {  // x1 is fixed for the life of this solver: slice it once
+    xs8_.alloc(i8_blob_bytes(t_local_));
+    wblob8_.alloc((size_t)I8_WBLOB_BYTES);
+    stats_.kernel_launches += i8_slice_x(d_x_, ldx_, t_local_, dims_.n, xs8_.p, st_);
+  }
   PICARD_CUDA(cudaEventRecord(ev_a_, st_));
-  stats_.kernel_launches += launch_pass(L);
+  stats_.kernel_launches += use_i8 ? launch_loss_i8(L, xs8_.p, wblob8_.p) : launch_pass(L);
   PICARD_CUDA(cudaEventRecord(ev_b_, st_));
   // one NCCL allreduce of exactly what this pass produced
   if (comm_ && comm_size(comm_) > 1) {

@@ -75,9 +75,18 @@ static __global__ void reduce_rb_kernel(const double* __restrict__ partial, int 
     }
     if (skip) continue;
     const int rb = row / rp;
-    double s = 0.0;
-    for (int k = 0; k < n_tg; ++k) s += partial[(size_t)(k * nrb + rb) * psz + src];
-    mom[dst] = s;
+    // eight independent chains (the loads of a chain step are in flight together: the kernel is latency-bound), combined in a
+    // fixed order: the result does not depend on the launch geometry
+    const double* pp = partial + (size_t)rb * psz + src;
+    const size_t kstride = (size_t)nrb * psz;
+    double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int k = 0;
+    for (; k + 8 <= n_tg; k += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += pp[(size_t)(k + u) * kstride];
+    }
+    for (int u = 0; k < n_tg; ++k, ++u) s[u] += pp[(size_t)k * kstride];
+    mom[dst] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   }
 }
 

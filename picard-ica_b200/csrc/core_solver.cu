@@ -187,11 +187,20 @@ void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
   const bool store = store_y && mode == PASS_LOSS && ybuf_.p != nullptr;
   L.d_out = store ? ybuf_.p : nullptr; L.ld_out = store ? ldx_ : 0;
   if (mode == PASS_LOSS) ybuf_valid_ = store;
-  const bool use_i8 = i8_enabled() && mode == PASS_LOSS && pass_padded_size(dims_.n) == 128;
+  // LOSS pass on the INT8 tensor cores (i8_loss.cu) for 64 < N <= 128: automatic on whitened data, PICARD_I8 = 0 / 1 overrides
+  bool use_i8 = mode == PASS_LOSS && pass_padded_size(dims_.n) == 128 && !i8_failed_ &&
+                (i8_mode() == 1 || (i8_mode() == -1 && cov_identity_));
   if (use_i8 && !xs8_.p) {  // x1 is fixed for the life of this solver: slice it once
-    xs8_.alloc(i8_blob_bytes(t_local_));
-    wblob8_.alloc((size_t)I8_WBLOB_BYTES);
-    stats_.kernel_launches += i8_slice_x(d_x_, ldx_, t_local_, dims_.n, xs8_.p, st_);
+    try {
+      xs8_.alloc(i8_blob_bytes(t_local_));
+      wblob8_.alloc((size_t)I8_WBLOB_BYTES);
+      stats_.kernel_launches += i8_slice_x(d_x_, ldx_, t_local_, dims_.n, xs8_.p, st_);
+    } catch (const Error&) {  // no memory for the sliced image: the FP64 path needs none
+      cudaGetLastError();
+      xs8_.release(); wblob8_.release();
+      i8_failed_ = true;
+      use_i8 = false;
+    }
   }
   PICARD_CUDA(cudaEventRecord(ev_a_, st_));
   stats_.kernel_launches += use_i8 ? launch_loss_i8(L, xs8_.p, wblob8_.p) : launch_pass(L);

@@ -137,7 +137,8 @@ class CoreSolver {
   double* w_try_ = nullptr;  // W' of the last evaluated try
   DevBuf<double> ybuf_;    // Y' of the last loss-only try (n x ldx_), empty when PICARD_FLAG_NO_Y_STORE or out of memory
   bool ybuf_valid_ = false;
-  DevBuf<uint8_t> xs8_, wblob8_;  // PICARD_I8=1: sliced INT8 image of x1 (built at the first LOSS pass) and of the trial W (i8_loss.cu)
+  DevBuf<uint8_t> xs8_, wblob8_;  // sliced INT8 image of x1 (built at the first LOSS pass) and of the trial W (i8_loss.cu)
+  bool i8_failed_ = false;
   DevBuf<CoreScalars> sc_dev_;
   PinnedBuf<CoreScalars> sc_host_;
   // views into store_

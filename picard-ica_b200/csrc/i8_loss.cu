@@ -1,7 +1,8 @@
 // =====================================================================================================
 // i8_loss.cu -- the LOSS pass (Y' = W' x1, log-likelihood / y^2 row sums, Y' kept in HBM: core.rs:124-127 with compute_loss
 // core.rs:39-85) on the INT8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM) instead of the FP64 DMMA path.
-// EXPERIMENT: selected with PICARD_I8=1 for 64 < N <= 128; the default path is rb_loss_kernel (rowblock.cuh).
+// Used for 64 < N <= 128 when the data is whitened (every component of a sample is O(1), so the per-sample scaling loses
+// nothing); PICARD_I8=0 selects the FP64 path (rb_loss_kernel, rowblock.cuh) everywhere, PICARD_I8=1 forces this one.
 //
 // Error-free splitting (Ozaki-type).  Every row of W' and every sample (column) of x1 is scaled by its own power of two into
 // (-1, 1) and cut into S = 7 signed 7-bit slices (q_p = trunc(128 r_p), r_{p+1} = 128 r_p - q_p: exact in f64), so
@@ -382,13 +383,13 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
 
 }  // namespace i8
 
-bool i8_enabled() {
-  static int v = -1;
-  if (v < 0) {
+int i8_mode() {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("PICARD_I8");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = !e ? -1 : (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : -1));
   }
-  return v != 0;
+  return v;
 }
 
 size_t i8_blob_bytes(int64_t t_local) { return (size_t)((t_local + I8_TILE - 1) / I8_TILE) * I8_TILE_BYTES; }

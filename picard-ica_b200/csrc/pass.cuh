@@ -184,7 +184,7 @@ pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p) {
   }
   for (int i = tid; i < NP; i += G::NTHREADS) bs[i] = (p.bias != nullptr && i < p.n_out) ? p.bias[i] : 0.0;
   if (NEED_TAB)
-    for (int i = tid; i < dmath::EXP_TAB_N; i += G::NTHREADS) { tab[i] = g_exp_tab[i]; tab[dmath::EXP_TAB_N + i] = g_log_tab[i]; }
+    load_density_tables<false>(tab, DENS == DENS_TANH, tid, G::NTHREADS);
   if (tid == 0) {
     ptx::prefetch_tmap(&tmap);
     for (int s = 0; s < G::STAGES; ++s) { ptx::mbar_init(&bar[s], 1); cnt[s] = 0; }

@@ -52,6 +52,7 @@ WORKLOADS = {
     "c5": dict(n=32, t=1_000_000, ortho=True, extended=True, kind=0, alpha=1.0, n_laplace=16, jade_it=50,
                desc="N=32,T=1e6 f64 jade_it=50 warm start then Picard-O extended (JADE runs inside the e2e fit)"),
 }
+I8_LOSS_TRAFFIC = 19.233e9  # dram bytes per launch of loss_i8_kernel at c3 from the ncu --set full capture (profiles/summary_r01i.txt)
 FP64_PEAK_TFLOPS = 37.19  # measured by us on this pool's B200 (profiles/microbench/fp64_pipes_r01.jsonl, DMMA m8n8k4);
 #                           MEASURED_PEAKS.json has no FP64 figure
 
@@ -327,16 +328,31 @@ def _main(out):
         name, flops, cnt, ms = max(cand, key=lambda c: c[3])
         avg_ms = ms / cnt
         ach = flops / (avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": {"loss": "rb_loss_kernel (LOSS + Y store)", "grady": "rb_grady_kernel (stored-Y gradient)"}.get(name, f"pass_kernel<{name}>"), "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+        # the LOSS pass of a whitened 64 < N <= 128 problem runs on the INT8 tensor cores (i8_loss.cu) unless PICARD_I8=0
+        i8 = name == "loss" and 64 < n <= 128 and os.environ.get("PICARD_I8", "") != "0"
+        kname = {"loss": "loss_i8_kernel (LOSS + Y store on tcgen05.mma kind::i8, 28 slice products)" if i8 else "rb_loss_kernel (LOSS + Y store)",
+                 "grady": "rb_grady_kernel (stored-Y gradient)"}.get(name, f"pass_kernel<{name}>")
+        roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": ach / FP64_PEAK_TFLOPS,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture at c3 on one GPU
                 # (profiles/summary_r01f.txt), scaled to this rank's share of the samples; null for kernels not captured
-                "traffic": {"loss": 20.436e9, "grady": 10.248e9}.get(name, None) and {"loss": 20.436e9, "grady": 10.248e9}[name] * (t_local / 1e7) * (n / 128.0)
+                "traffic": {"loss": I8_LOSS_TRAFFIC if i8 else 20.436e9, "grady": 10.248e9}.get(name, None) and
+                {"loss": I8_LOSS_TRAFFIC if i8 else 20.436e9, "grady": 10.248e9}[name] * (t_local / 1e7) * (n / 128.0)
                 if (n == 128) else None,
-                "algorithmic_bytes": (16.0 if name == "loss" else 8.0) * n * t_local, "avg_launch_ms": avg_ms, "launches": cnt,
+                # LOSS: read x1 (8 B / element; its 7-slice INT8 image is 7.06 B / element) and write Y' (8 B); gradient: read Y'
+                "algorithmic_bytes": ((15.0625 if i8 else 16.0) if name == "loss" else 8.0) * n * t_local, "avg_launch_ms": avg_ms, "launches": cnt,
                 "flops_per_launch": flops, "peak_source": "FP64 DMMA m8n8k4 microbenchmark measured by us "
                 "(profiles/microbench/fp64_pipes_r01.jsonl); MEASURED_PEAKS.json has no FP64 entry",
                 "share_of_step": ms / dev_ms, "hbm_gbs": 8.0 * n * t_local / (avg_ms * 1e-3) / 1e9}
+        if i8:
+            # achieved / peak above stay on the ALGORITHMIC f64 flops of the pass (2 N^2 T) against the FP64 tensor peak -- the
+            # roofline BASELINE.md defines; what the tensor cores actually execute is 28 INT8 products of that shape:
+            ops = 28.0 * 2.0 * 128 * 128 * t_local
+            roof["engine"] = {"what": "error-free 7-slice INT8 splitting, s32 accumulators in TMEM, result within 2e-13 of f64 (tools/ozaki_numerics.py)",
+                              "int8_tops": ops / (avg_ms * 1e-3) / 1e12, "int8_peak_nominal_tops": 4500.0,
+                              "int8_ceiling_for_128x32x32_mma_tops": 1484.8,
+                              "ceiling_source": "profiles/microbench/umma_i8_probe_r01.jsonl: 51 cycles per MMA whatever N <= 64; TMEM (512 columns) "
+                                                "holds 7 level accumulators + the W' slices only for N = 32"}
     pass_mix = {"fused": d["fused_passes"], "grad": d["grad_passes"], "loss": d["loss_passes"], "ls_tries": d["ls_tries"],
                 "fallbacks": d["fallbacks"], "sign_changes": d["sign_changes"], "restarts": restarts, "grady": d["grady_passes"],
                 "pass_ms": {"fused": d["pass_ms_fused"], "grad": d["pass_ms_grad"], "loss": d["pass_ms_loss"], "grady": d["pass_ms_grady"]}}

@@ -104,9 +104,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
 }
-// exact conversion of |v| < 2^51 on the ALU + one DADD (I2F.F64.S64 is a slow-path instruction)
-__device__ __forceinline__ double i64_to_f64(long long v) {
-  return __longlong_as_double(0x4338000000000000ll + v) - 6755399441055744.0;
+// v 2^k on the ALU (v = 0 or a normal double far from the exponent limits): every FP64-pipe instruction of the epilogue competes
+// with the tensor core for the pipe (ncu: 57 % of the epilogue's warp samples wait on the math pipe while it is 15 % active)
+__device__ __forceinline__ double scale_pow2(double v, int k) {
+  const int h = __double2hiint(v), l = __double2loint(v);
+  return (((h << 1) | l) != 0) ? __hiloint2double(h + (k << 20), l) : v;
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -287,7 +289,7 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_full);
     }
-    const double rs = reinterpret_cast<const double*>(wblob + (size_t)S * SLICE_A_BYTES)[row];
+    const int rexp = (__double2hiint(reinterpret_cast<const double*>(wblob + (size_t)S * SLICE_A_BYTES)[row]) >> 20) - 1023;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int st = (int)(it % NSTAGE);
       const int64_t t0 = (tile0 + it * tstride) * NT + CPT * cq;
@@ -315,15 +317,15 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
         for (int d = 4; d < S; ++d) lo = lo * 128 + (long long)c[d][e];
 #pragma unroll
         for (int d = S; d < 7; ++d) lo = lo * 128;
-        y[e] = fma(i64_to_f64(lo), 3.7252902984619140625e-09 /* 2^-28 */, i64_to_f64(hi));
+        y[e] = fma((double)lo, 3.7252902984619140625e-09 /* 2^-28 */, (double)hi);  // I2F.F64.S64: not an FP64-pipe instruction
       }
       // column scales of this thread's samples (bulk-copied with the tile: wait on its barrier for visibility; complete long ago),
       // then the ring stage goes back to the producer
       ptx::mbar_wait(&b_full[st], (uint32_t)((it / NSTAGE) & 1));
       {
-        const double* csm = reinterpret_cast<const double*>(sb + (size_t)st * STAGE_BYTES + (size_t)S * SLICE_B_BYTES) + CPT * cq;
+        const int* csm = reinterpret_cast<const int*>(sb + (size_t)st * STAGE_BYTES + (size_t)S * SLICE_B_BYTES) + 2 * CPT * cq;
 #pragma unroll
-        for (int e = 0; e < CPT; ++e) y[e] *= csm[e] * rs;
+        for (int e = 0; e < CPT; ++e) y[e] = scale_pow2(y[e], rexp + (csm[2 * e + 1] >> 20) - 1023);  // scales are exact powers of two
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&b_empty[st]);

@@ -271,7 +271,7 @@ struct Prefault {
     const size_t bytes = sizeof(double) * count;
     if (bytes < ((size_t)64 << 20)) return;
     unsigned hw = std::thread::hardware_concurrency();
-    const int n = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 2u));
+    const int n = (int)std::max(1u, std::min(16u, hw ? hw / 2 : 2u));
     unsigned char* base = reinterpret_cast<unsigned char*>(p);
     const size_t per = ((bytes / n) + 4095) & ~(size_t)4095;
     for (int t = 0; t < n; ++t) {
@@ -283,6 +283,16 @@ struct Prefault {
   void join() { for (auto& t : th) if (t.joinable()) t.join(); th.clear(); }
   ~Prefault() { join(); }
 };
+
+// fit_host knows the shape of `sources` before the H2D copy starts: it allocates the result and starts the page faults there,
+// so that they also overlap the upload and the preprocessing; fit_device adopts the buffer (same thread) if the size matches.
+struct PendingResult {
+  double* p = nullptr;
+  size_t count = 0;
+  Prefault pf;
+  void drop() { pf.join(); free(p); p = nullptr; count = 0; }
+};
+static thread_local PendingResult* g_pending_result = nullptr;
 
 static double* dup_host(const double* p, size_t n) {
   double* o = (double*)malloc(sizeof(double) * (n ? n : 1));
@@ -420,8 +430,14 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   struct HostBuf { double* p = nullptr; ~HostBuf() { free(p); } double* release() { double* q = p; p = nullptr; return q; } } src_guard;
   Prefault prefault;
   if (!keep_dev) {
-    src_guard.p = alloc_result((size_t)nc * t_local);
-    prefault.start(src_guard.p, (size_t)nc * t_local);
+    PendingResult* pr = g_pending_result;
+    if (pr && pr->p && pr->count == (size_t)nc * t_local) {  // allocated (and being faulted in) since before the upload
+      src_guard.p = pr->p; pr->p = nullptr; pr->count = 0;
+      prefault.th = std::move(pr->pf.th);
+    } else {
+      src_guard.p = alloc_result((size_t)nc * t_local);
+      prefault.start(src_guard.p, (size_t)nc * t_local);
+    }
   }
   if (cfg.verbose && (!cfg.comm || comm_rank(cfg.comm) == 0)) printf("Running Picard...\n");
   CoreSolver core(x1.p, nc, t_local, ld1, cfg, extended && cfg.whiten, guard.sm_count, st);  // solver.rs:143-166
@@ -484,6 +500,19 @@ void fit_host(const double* x, int64_t n_features, int64_t n_samples, int64_t ro
   if (n_features <= 0 || n_samples <= 0 || x == nullptr)
     throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
   DeviceGuard guard(cfg.device);
+  // shape of the result when it does not depend on the other ranks: nc = n_components (whitening) or n_features
+  PendingResult pending;
+  struct PendingGuard { PendingResult* r; ~PendingGuard() { g_pending_result = nullptr; r->drop(); } } pending_guard{&pending};
+  if (n_features <= n_samples) {
+    const int64_t ncomp = cfg.n_components >= 0 ? std::min<int64_t>(cfg.n_components, n_features) : n_features;
+    const int64_t nc = cfg.whiten ? ncomp : n_features;
+    if (nc > 0) {
+      pending.count = (size_t)nc * (size_t)n_samples;
+      pending.p = alloc_result(pending.count);
+      pending.pf.start(pending.p, pending.count);
+      g_pending_result = &pending;
+    }
+  }
   const int64_t ldx = round_up(n_samples, 16);
   DevBuf<double> dx((size_t)n_features * ldx);
   cudaEvent_t e0, e1;

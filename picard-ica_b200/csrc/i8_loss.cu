@@ -48,6 +48,12 @@ constexpr int STAGE_BYTES = ((TILE_BYTES + 1023) / 1024) * 1024;
 constexpr int SLICE_A_BYTES = 128 * KP;  // 16384
 constexpr int NSTAGE = 2;
 constexpr int ACC_COLS = S * NT;         // 224 TMEM columns: the 7 level accumulators of one tile
+#ifdef I8_TWO_GROUPS   // A/B build: the level accumulators handed over in two groups (levels 0-4: 60 MMAs, 5-6: 52 MMAs)
+constexpr int NGROUP = 2;
+#else
+constexpr int NGROUP = 1;
+#endif
+__host__ __device__ constexpr int group_begin(int g) { return NGROUP == 1 ? (g == 0 ? 0 : S) : (g == 0 ? 0 : (g == 1 ? 5 : S)); }
 constexpr int TMEM_A = ACC_COLS;         // W' slices live in tensor memory too: slice p, K-step k at column TMEM_A + 8 (4 p + k)
 constexpr int NEW = 16;                  // epilogue warps: TMEM lane quarter (warp & 3) x column quarter of the tile (warp >> 2)
 constexpr int CPT = NT / (NEW / 4);      // samples per epilogue thread and tile (8)
@@ -205,10 +211,11 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
   uint64_t* b_full = bars + 1;             // NSTAGE
   uint64_t* b_empty = b_full + NSTAGE;     // NSTAGE : MMA commit + the 8 epilogue warps (they read the column scales)
   // ONE accumulator set (there is no room for two next to the W' slices in tensor memory): the epilogue reads it back at once and
-  // returns it before it combines the levels.  Handing the levels over in two groups was measured slower (9.8 vs 9.3 ms).
-  uint64_t* acc_full = b_empty + NSTAGE;   // accumulators of a tile complete (MMA commit)
-  uint64_t* acc_empty = acc_full + 1;      // accumulators read back (NEW epilogue warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  // returns it before it combines the levels.  Handing the levels over in two groups (-DI8_TWO_GROUPS) was measured slower twice
+  // (9.8 vs 9.3 ms with direct stores, 8.66 vs 8.39 ms with the TMA-store path): the pass is bound by its epilogue, not by the hand-over.
+  uint64_t* acc_full = b_empty + NSTAGE;   // [NGROUP] accumulators (of a level group) of a tile complete (MMA commit)
+  uint64_t* acc_empty = acc_full + 2;      // [NGROUP] accumulators read back (NEW epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr bool NEED_TAB = (DENS == DENS_TANH || DENS == DENS_EXP);
@@ -216,8 +223,7 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
   if (tid == 0) {
     ptx::mbar_init(a_full, 4);
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1 + NEW); }
-    ptx::mbar_init(acc_full, 1);
-    ptx::mbar_init(acc_empty, NEW);
+    for (int g = 0; g < NGROUP; ++g) { ptx::mbar_init(&acc_full[g], 1); ptx::mbar_init(&acc_empty[g], NEW); }
     ptx::fence_barrier_init();
   }
   if (warp == NEW + 1) {  // the MMA warp owns the tensor memory: all 512 columns (one CTA per SM)
@@ -250,22 +256,25 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
         const int st = (int)(it % NSTAGE);
         ptx::mbar_wait(&b_full[st], (uint32_t)((it / NSTAGE) & 1));
         const uint64_t db0 = make_desc(smem_u32(sb + (size_t)st * STAGE_BYTES));
-        ptx::mbar_wait(acc_empty, (uint32_t)((it & 1) ^ 1));  // the epilogue has read tile it - 1 back (first tile: passes)
-        tc_fence_after();
 #pragma unroll
-        for (int d = 0; d < S; ++d) {
-          const uint32_t tacc = tmem + (uint32_t)(d * NT);
+        for (int g = 0; g < NGROUP; ++g) {
+          ptx::mbar_wait(&acc_empty[g], (uint32_t)((it & 1) ^ 1));  // the epilogue has read this group of tile it - 1 back (first tile: passes)
+          tc_fence_after();
 #pragma unroll
-          for (int pa = 0; pa <= d; ++pa) {
-            const int qb = d - pa;
+          for (int d = group_begin(g); d < group_begin(g + 1); ++d) {
+            const uint32_t tacc = tmem + (uint32_t)(d * NT);
 #pragma unroll
-            for (int k = 0; k < KP / 32; ++k)
-              umma_i8(tacc, tmem + (uint32_t)(TMEM_A + 8 * (4 * pa + k)), db0 + (uint64_t)((qb * SLICE_B_BYTES + k * 32) >> 4),
-                      (pa > 0 || k > 0) ? 1u : 0u);
+            for (int pa = 0; pa <= d; ++pa) {
+              const int qb = d - pa;
+#pragma unroll
+              for (int k = 0; k < KP / 32; ++k)
+                umma_i8(tacc, tmem + (uint32_t)(TMEM_A + 8 * (4 * pa + k)), db0 + (uint64_t)((qb * SLICE_B_BYTES + k * 32) >> 4),
+                        (pa > 0 || k > 0) ? 1u : 0u);
+            }
           }
+          if (g == NGROUP - 1) umma_commit(&b_empty[st]);  // the ring stage may be refilled once these MMAs have read it (and the epilogue its scales)
+          umma_commit(&acc_full[g]);                       // this group's accumulators complete
         }
-        umma_commit(&b_empty[st]);  // the ring stage may be refilled once these MMAs have read it (and the epilogue its scales)
-        umma_commit(acc_full);      // accumulators of this tile complete
       }
     }
   } else {
@@ -295,17 +304,18 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
       const int64_t t0 = (tile0 + it * tstride) * NT + CPT * cq;
       // the level accumulators of this thread's 8 samples; then the accumulators go back to the MMA warp
       int32_t c[S][8];
-      ptx::mbar_wait(acc_full, (uint32_t)(it & 1));
-      tc_fence_after();
-      {
-        const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(CPT * cq);
+      const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(CPT * cq);
 #pragma unroll
-        for (int d = 0; d < S; ++d) tmem_ld8(taddr + (uint32_t)(d * NT), c[d]);
+      for (int g = 0; g < NGROUP; ++g) {
+        ptx::mbar_wait(&acc_full[g], (uint32_t)(it & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int d = group_begin(g); d < group_begin(g + 1); ++d) tmem_ld8(taddr + (uint32_t)(d * NT), c[d]);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[g]);
       }
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(acc_empty);
       double y[CPT];
 #pragma unroll
       for (int e = 0; e < CPT; ++e) {

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PICARD_B200_ABI_VERSION 1
+#define PICARD_B200_ABI_VERSION 2
 
 /* PicardError (error.rs:9-42).  NotConverged is never constructed by the reference (non-convergence
  * returns Ok{converged:false}), so it has no status code here either. */
@@ -73,6 +73,10 @@ typedef struct {
 #define PICARD_FLAG_KEEP_SOURCES_ON_DEVICE 2u /* picard_fit_device: do not copy `sources` to the host */
 #define PICARD_FLAG_FORCE_SPECULATION 8u /* speculative fused first try even though the Y store is available (ablation) */
 #define PICARD_FLAG_NO_Y_STORE 4u /* loss-only tries do not keep Y' (saves one N x T buffer; the gradient recomputes W X) */
+/* The passes of a whitened problem with 64 < N <= 128 run on the INT8 tensor cores (error-free splitting, results within
+ * ~1e-13 of the FP64 path) when a range check of the data passes; these two flags override the choice. */
+#define PICARD_FLAG_NO_INT8 16u    /* FP64 (DMMA) kernels only */
+#define PICARD_FLAG_FORCE_INT8 32u /* INT8 passes even if the data is not flagged as whitened / fails the range check */
 
 /* Measurement record filled by every fit / core run (not in the reference). */
 typedef struct {
@@ -86,6 +90,10 @@ typedef struct {
   double pass_ms_fused, pass_ms_grad, pass_ms_loss; /* summed device time of the pass kernels by kind */
   int64_t grady_passes;    /* gradient passes served from the stored Y of an accepted loss-only try (2 N^2 T flop) */
   double pass_ms_grady;
+  int64_t i8_loss_passes;  /* of loss_passes: run on the INT8 tensor cores (tcgen05.mma kind::i8) */
+  int64_t i8_grad_passes;  /* of grady_passes: run on the INT8 tensor cores */
+  int64_t i8_fallbacks;    /* 1 if the INT8 path was wanted but refused: range check of the data failed, or no memory for the sliced image */
+  double i8_range;         /* the range check's figure: mean power-of-two sample bound / smallest row RMS of x1 (0 = not evaluated) */
 } picard_stats_t;
 
 /* PicardResult (result.rs:7-33).  Buffers are malloc'd by the library and released by
@@ -160,12 +168,23 @@ void picard_core_destroy(picard_core_t* c);
 int picard_eval_moments(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
                         int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device, double* gr,
                         double* sd, double* hr, double* sq, double* lrow, char* err, size_t errlen);
+/* picard_eval_moments with explicit execution flags (PICARD_FLAG_NO_INT8 / FORCE_INT8 ...) and the `whitened` promise of
+ * core::run's covariance = Some(I); stats (may be NULL) reports which engine ran (i8_loss_passes, i8_grad_passes, i8_fallbacks). */
+int picard_eval_moments_ex(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
+                           int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device, uint32_t flags,
+                           int32_t whitened, double* gr, double* sd, double* hr, double* sq, double* lrow, picard_stats_t* stats,
+                           char* err, size_t errlen);
 /* Same on a DEVICE-resident matrix, `repeats` launches timed with CUDA events on the library's stream
  * (avg_ms = mean duration of one pass incl. the partial reduction).  Bench / profiling hook. */
 int picard_eval_moments_device(const double* d_x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
                                int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device,
                                int32_t repeats, double* avg_ms, double* gr, double* sd, double* hr, double* sq, double* lrow,
                                char* err, size_t errlen);
+/* ... with execution flags and the `whitened` promise (bench.py's parity block compares the INT8 and FP64 engines with it). */
+int picard_eval_moments_device_ex(const double* d_x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
+                                  int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device, uint32_t flags,
+                                  int32_t whitened, int32_t repeats, double* avg_ms, double* gr, double* sd, double* hr, double* sq,
+                                  double* lrow, picard_stats_t* stats, char* err, size_t errlen);
 /* The processed quantities of one iteration front (core.rs:215-293) plus the loss (core.rs:39-85) at
  * Y = W X: projected gradient g, Hessian approximation h, h_off, signs, sign_change, gradient norm, loss.
  * c = C matrix of the extended sign rule (NULL = identity); old_signs NULL = first iteration;

@@ -16,11 +16,12 @@ from typing import Optional
 import numpy as np
 
 from . import _ffi
-from ._ffi import FLAG_KEEP_SOURCES_ON_DEVICE, FLAG_FORCE_SPECULATION, FLAG_NO_SPECULATION, FLAG_NO_Y_STORE, LibraryMissing
+from ._ffi import (FLAG_FORCE_INT8, FLAG_FORCE_SPECULATION, FLAG_KEEP_SOURCES_ON_DEVICE, FLAG_NO_INT8, FLAG_NO_SPECULATION,
+                   FLAG_NO_Y_STORE, LibraryMissing)
 
 __all__ = [
     "Picard", "PicardConfig", "ConfigBuilder", "DensityType", "Tanh", "Exp", "Cube", "PicardResult", "PicardError", "utils",
-    "CoreLoop", "FLAG_NO_SPECULATION", "FLAG_KEEP_SOURCES_ON_DEVICE", "FLAG_NO_Y_STORE", "FLAG_FORCE_SPECULATION", "LibraryMissing",
+    "CoreLoop", "FLAG_NO_SPECULATION", "FLAG_KEEP_SOURCES_ON_DEVICE", "FLAG_NO_Y_STORE", "FLAG_FORCE_SPECULATION", "FLAG_NO_INT8", "FLAG_FORCE_INT8", "LibraryMissing",
 ]
 
 _dp = _ffi.dp

@@ -14,7 +14,8 @@ dp = C.POINTER(C.c_double)
 EXPORTED = [
     "picard_abi_version", "picard_device_count", "picard_status_string", "picard_release_cache", "picard_config_default", "picard_config_validate",
     "picard_fit", "picard_fit_device", "picard_transform", "picard_result_free", "picard_core_create", "picard_core_run",
-    "picard_core_reset", "picard_core_state", "picard_core_stats", "picard_core_destroy", "picard_eval_moments", "picard_eval_moments_device",
+    "picard_core_reset", "picard_core_state", "picard_core_stats", "picard_core_destroy", "picard_eval_moments", "picard_eval_moments_ex",
+    "picard_eval_moments_device", "picard_eval_moments_device_ex",
     "picard_eval_point", "picard_matrix_exp", "picard_sln_det", "picard_sym_decorrelation", "picard_compute_direction",
     "picard_center_whiten", "picard_center_whiten_device", "picard_jade", "picard_jade_cumulants", "picard_synth_sources", "picard_apply_device", "picard_comm_unique_id",
     "picard_comm_create", "picard_comm_rank", "picard_comm_size", "picard_comm_destroy",
@@ -40,6 +41,7 @@ class Stats(C.Structure):  # picard_stats_t
         ("ls_tries", C.c_int64), ("fallbacks", C.c_int64), ("sign_changes", C.c_int64), ("kernel_launches", C.c_int64),
         ("pass_ms_fused", C.c_double), ("pass_ms_grad", C.c_double), ("pass_ms_loss", C.c_double),
         ("grady_passes", C.c_int64), ("pass_ms_grady", C.c_double),
+        ("i8_loss_passes", C.c_int64), ("i8_grad_passes", C.c_int64), ("i8_fallbacks", C.c_int64), ("i8_range", C.c_double),
     ]
 
     def as_dict(self):
@@ -59,6 +61,8 @@ FLAG_NO_SPECULATION = 1
 FLAG_KEEP_SOURCES_ON_DEVICE = 2
 FLAG_NO_Y_STORE = 4
 FLAG_FORCE_SPECULATION = 8
+FLAG_NO_INT8 = 16
+FLAG_FORCE_INT8 = 32
 UNIQUE_ID_BYTES = 128
 
 _lib = None

@@ -180,37 +180,48 @@ void picard_core_destroy(picard_core_t* c) {
 }
 
 // ---- test hooks -----------------------------------------------------------------------------------
-int picard_eval_moments(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w, int32_t density_kind,
-                        double alpha, int32_t mode, int32_t want_h, int32_t device, double* gr, double* sd, double* hr, double* sq,
-                        double* lrow, char* err, size_t errlen) {
+int picard_eval_moments_ex(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w, int32_t density_kind,
+                           double alpha, int32_t mode, int32_t want_h, int32_t device, uint32_t flags, int32_t whitened, double* gr,
+                           double* sd, double* hr, double* sq, double* lrow, picard_stats_t* stats, char* err, size_t errlen) {
   return guarded(err, errlen, [&] {
     if (mode < 0 || mode > 3) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'mode': must be 0, 1, 2 or 3");
     DeviceGuard guard(device);
     Staged xs(x, n, n_samples, row_stride, 0);
     PICARD_CUDA(cudaStreamSynchronize(0));
     picard_config_t c = hook_config(density_kind, alpha, want_h ? 0 : 1, 0, 0.01, guard.device);
+    c.flags = flags;
     config_validate(c);
     cudaStream_t st;
     PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
-    CoreSolver solver(xs.buf.p, (int)n, n_samples, xs.ld, c, false, guard.sm_count, st);
+    CoreSolver solver(xs.buf.p, (int)n, n_samples, xs.ld, c, whitened != 0, guard.sm_count, st);
     solver.hook_moments(w, mode, want_h != 0, gr, sd, hr, sq, lrow);
+    if (stats) *stats = solver.stats();
   });
 }
 
-int picard_eval_moments_device(const double* d_x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
-                               int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device, int32_t repeats,
-                               double* avg_ms, double* gr, double* sd, double* hr, double* sq, double* lrow, char* err, size_t errlen) {
+int picard_eval_moments(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w, int32_t density_kind,
+                        double alpha, int32_t mode, int32_t want_h, int32_t device, double* gr, double* sd, double* hr, double* sq,
+                        double* lrow, char* err, size_t errlen) {
+  return picard_eval_moments_ex(x, n, n_samples, row_stride, w, density_kind, alpha, mode, want_h, device, 0u, 0, gr, sd, hr, sq, lrow,
+                                nullptr, err, errlen);
+}
+
+int picard_eval_moments_device_ex(const double* d_x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
+                                  int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device, uint32_t flags,
+                                  int32_t whitened, int32_t repeats, double* avg_ms, double* gr, double* sd, double* hr, double* sq,
+                                  double* lrow, picard_stats_t* stats, char* err, size_t errlen) {
   return guarded(err, errlen, [&] {
     if (mode < 0 || mode > 4) throw Error(PICARD_INVALID_CONFIG, "Invalid configuration for 'mode': must be 0..4");
     if (n <= 0 || n_samples <= 0 || !d_x) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: Input matrix cannot be empty");
     DeviceGuard guard(device);
     picard_config_t c = hook_config(density_kind, alpha, want_h ? 0 : 1, 0, 0.01, guard.device);
+    c.flags = flags;
     config_validate(c);
     cudaStream_t st;
     PICARD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{st};
-    CoreSolver solver(d_x, (int)n, n_samples, row_stride, c, false, guard.sm_count, st);
+    CoreSolver solver(d_x, (int)n, n_samples, row_stride, c, whitened != 0, guard.sm_count, st);
     // mode 4 = the stored-Y gradient kernel alone: fill the store first (mode 3 = loss pass with store + grady)
     solver.hook_moments(w, mode == 4 ? 3 : mode, want_h != 0, gr, sd, hr, sq, lrow);  // warm-up + results
     if (repeats > 0) {
@@ -225,7 +236,15 @@ int picard_eval_moments_device(const double* d_x, int64_t n, int64_t n_samples, 
       cudaEventDestroy(e0); cudaEventDestroy(e1);
       if (avg_ms) *avg_ms = ms / repeats;
     }
+    if (stats) *stats = solver.stats();
   });
+}
+
+int picard_eval_moments_device(const double* d_x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w,
+                               int32_t density_kind, double alpha, int32_t mode, int32_t want_h, int32_t device, int32_t repeats,
+                               double* avg_ms, double* gr, double* sd, double* hr, double* sq, double* lrow, char* err, size_t errlen) {
+  return picard_eval_moments_device_ex(d_x, n, n_samples, row_stride, w, density_kind, alpha, mode, want_h, device, 0u, 0, repeats, avg_ms,
+                                       gr, sd, hr, sq, lrow, nullptr, err, errlen);
 }
 
 int picard_eval_point(const double* x, int64_t n, int64_t n_samples, int64_t row_stride, const double* w, int32_t density_kind,

@@ -5,6 +5,8 @@
 
 #include <dlfcn.h>
 
+#include <mutex>
+
 namespace picard {
 
 namespace {
@@ -28,9 +30,8 @@ struct NcclApi {
 
 NcclApi& api() {
   static NcclApi a;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
       a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
       if (a.handle) break;
@@ -44,7 +45,7 @@ NcclApi& api() {
       a.group_start = (GroupFn)dlsym(a.handle, "ncclGroupStart");
       a.group_end = (GroupFn)dlsym(a.handle, "ncclGroupEnd");
     }
-  }
+  });
   if (!a.handle || !a.get_unique_id || !a.comm_init_rank || !a.comm_destroy || !a.all_reduce)
     throw Error(PICARD_COMPUTATION_ERROR, "Computation error: NCCL (libnccl.so.2) could not be loaded");
   return a;

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
+#include <atomic>
 #include <string>
 
 #include "../../include/picard_b200.h"
@@ -27,6 +28,23 @@ struct Error : std::runtime_error {
   } while (0)
 
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// Per-device, thread-safe cache of a launch constant (blocks per SM after cudaFuncSetAttribute, or just "configured").
+// Function attributes and occupancy are properties of (kernel, device): a process-wide static would leave the kernel
+// unconfigured on the second device a process fits on.  compute() is idempotent, so a benign race only repeats it.
+struct PerDeviceInt {
+  static constexpr int kMaxDevices = 64;
+  std::atomic<int> v[kMaxDevices] = {};  // 0 = not computed yet on that device
+  template <typename F>
+  int get(F&& compute) {
+    int dev = 0;
+    PICARD_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return compute();
+    int x = v[dev].load(std::memory_order_acquire);
+    if (x == 0) { x = compute(); v[dev].store(x, std::memory_order_release); }
+    return x;
+  }
+};
 
 // Density kinds on the device. LINEAR (psi(y) = y) is internal: it turns the moments pass into the
 // covariance SYRK of the whitening step (whitening.rs:61 replacement).

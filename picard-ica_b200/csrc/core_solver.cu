@@ -1,15 +1,18 @@
 // The core Picard loop (core.rs:162-401) with device-resident state.
 //
 // Control flow is the reference's, quirk for quirk; what differs is where the work happens:
-//   * every N x T quantity comes from the fused pass (pass.cuh) reading X once: Y is never materialised,
-//     the transform of a line-search try is folded into W (Y' = (M W) X),
-//   * line-search tries are SPECULATIVE: the first try of an iteration also accumulates the gradient
-//     moments of the trial point, so an accepted first try (the common case) makes the next iteration's
-//     gradient pass free.  Retries use the loss-only variant.  The iterate sequence is unchanged.
+//   * the transform of a line-search try is folded into W: every try is ONE LOSS pass Y' = (M W) x1 that keeps Y' in HBM
+//     (the "Y store", one extra N x T buffer) and returns the log-likelihood / y^2 row sums; only an ACCEPTED try is
+//     followed by the stored-Y gradient pass (psi(Y') Y'^T, sum psi' [, psi'(Y') (Y'^2)^T]).  Nothing is computed for a
+//     rejected point.  Without the store (no memory, PICARD_FLAG_NO_Y_STORE) the first try of an iteration runs the fused
+//     from-X pass speculatively instead (pass.cuh);
+//   * for whitened problems with 64 < N <= 128 both passes run on the INT8 tensor cores (i8_loss.cu, i8_grad.cu: error-free
+//     digit splitting, results within ~1e-13 of the FP64 kernels -- three orders inside the parity bar, but not bit-identical
+//     to them, so the iterates of the two engines agree to that level, not to the last bit) after a range check of the data;
 //   * the per-row log-likelihood sums L_i are kept with each point, so the loss under new signs
 //     (core.rs:317-329) and the initial loss (core.rs:185) need no extra pass.
 #include "engine.cuh"
-#include "i8_loss.cuh"
+#include "i8.cuh"
 
 #include <chrono>
 #include <map>
@@ -179,6 +182,48 @@ void CoreSolver::reset() {
   gradient_norm_ = 1.0; current_loss_ = 0.0;
 }
 
+// Decides, once per solver, whether the two passes run on the INT8 tensor cores, and prepares the digit image of x1.
+//   wanted : the data is whitened (covariance = I promised by the caller) or PICARD_FLAG_FORCE_INT8 / PICARD_I8=1
+//   allowed: 64 < N <= 128, no PICARD_FLAG_NO_INT8 / PICARD_I8=0, memory for the image, and -- unless forced -- the RANGE CHECK:
+//            a sample is scaled by the power of two above its largest component, so a component loses the bits between that bound
+//            and its own magnitude.  range = (mean bound over the samples) / (smallest row RMS of x1) is ~4 for whitened data
+//            (every row has unit variance, the largest of 128 components of a sample is ~3); above 64 the FP64 kernels are used
+//            (stats.i8_fallbacks = 1): the promise "whitened" is not taken on trust.
+bool CoreSolver::i8_prepare() {
+  if (i8_state_ != 0) return i8_state_ == 1;
+  i8_state_ = -1;
+  const int env = i8_env_mode();
+  const bool forced = (cfg_.flags & PICARD_FLAG_FORCE_INT8) != 0 || env == 1;
+  if (pass_padded_size(dims_.n) != 128 || (cfg_.flags & PICARD_FLAG_NO_INT8) != 0 || env == 0) return false;
+  if (!forced && !cov_identity_) return false;
+  try {
+    xs8_.alloc(i8_blob_bytes(t_local_));
+    wblob8_.alloc((size_t)I8_WBLOB_BYTES);
+    xstats_.alloc((size_t)I8_XSTATS);
+    rowexp_.alloc(128);
+  } catch (const Error&) {  // no memory for the digit image: the FP64 kernels need none
+    cudaGetLastError();
+    xs8_.release(); wblob8_.release(); xstats_.release(); rowexp_.release();
+    stats_.i8_fallbacks = 1;
+    return false;
+  }
+  stats_.kernel_launches += i8_slice_x(d_x_, ldx_, t_local_, dims_.n, xs8_.p, xstats_.p, sm_count_, st_);
+  std::vector<double> hs((size_t)I8_XSTATS);
+  PICARD_CUDA(cudaMemcpyAsync(hs.data(), xstats_.p, sizeof(double) * I8_XSTATS, cudaMemcpyDeviceToHost, st_));
+  PICARD_CUDA(cudaStreamSynchronize(st_));
+  double min_ms = INFINITY;
+  for (int k = 0; k < dims_.n; ++k) min_ms = std::fmin(min_ms, hs[2 + k] / (double)t_local_);
+  const double mean_bound = hs[0] / (double)t_local_;
+  stats_.i8_range = min_ms > 0.0 ? mean_bound / std::sqrt(min_ms) : INFINITY;
+  if (!forced && !(stats_.i8_range <= 64.0)) {
+    xs8_.release(); wblob8_.release();
+    stats_.i8_fallbacks = 1;
+    return false;
+  }
+  i8_state_ = 1;
+  return true;
+}
+
 void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, double alpha, double* d_mom, bool store_y) {
   PassLaunch L;
   L.d_x = (mode == PASS_GRADY) ? ybuf_.p : d_x_; L.ldx = ldx_; L.t_local = t_local_; L.n_in = dims_.n; L.n_out = dims_.n;
@@ -187,23 +232,14 @@ void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
   const bool store = store_y && mode == PASS_LOSS && ybuf_.p != nullptr;
   L.d_out = store ? ybuf_.p : nullptr; L.ld_out = store ? ldx_ : 0;
   if (mode == PASS_LOSS) ybuf_valid_ = store;
-  // LOSS pass on the INT8 tensor cores (i8_loss.cu) for 64 < N <= 128: automatic on whitened data, PICARD_I8 = 0 / 1 overrides
-  bool use_i8 = mode == PASS_LOSS && pass_padded_size(dims_.n) == 128 && !i8_failed_ &&
-                (i8_mode() == 1 || (i8_mode() == -1 && cov_identity_));
-  if (use_i8 && !xs8_.p) {  // x1 is fixed for the life of this solver: slice it once
-    try {
-      xs8_.alloc(i8_blob_bytes(t_local_));
-      wblob8_.alloc((size_t)I8_WBLOB_BYTES);
-      stats_.kernel_launches += i8_slice_x(d_x_, ldx_, t_local_, dims_.n, xs8_.p, st_);
-    } catch (const Error&) {  // no memory for the sliced image: the FP64 path needs none
-      cudaGetLastError();
-      xs8_.release(); wblob8_.release();
-      i8_failed_ = true;
-      use_i8 = false;
-    }
-  }
+  // INT8 tensor-core engines (i8_loss.cu / i8_grad.cu) for whitened problems with 64 < N <= 128
+  const bool use_i8 = mode == PASS_LOSS && dens != DENS_LINEAR && i8_prepare();
+  const bool use_i8_grad = mode == PASS_GRADY && i8_state_ == 1 && i8_grad_supported(dims_.n, dens, want_h);
+  if (use_i8_grad) stats_.kernel_launches += i8_row_exponents(d_w, dims_.n, xstats_.p, rowexp_.p, st_);
   PICARD_CUDA(cudaEventRecord(ev_a_, st_));
-  stats_.kernel_launches += use_i8 ? launch_loss_i8(L, xs8_.p, wblob8_.p) : launch_pass(L);
+  if (use_i8) { stats_.kernel_launches += launch_loss_i8(L, xs8_.p, wblob8_.p); stats_.i8_loss_passes++; }
+  else if (use_i8_grad) { stats_.kernel_launches += launch_grad_i8(L, rowexp_.p); stats_.i8_grad_passes++; }
+  else stats_.kernel_launches += launch_pass(L);
   PICARD_CUDA(cudaEventRecord(ev_b_, st_));
   // one NCCL allreduce of exactly what this pass produced
   if (comm_ && comm_size(comm_) > 1) {

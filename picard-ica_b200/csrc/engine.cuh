@@ -137,8 +137,12 @@ class CoreSolver {
   double* w_try_ = nullptr;  // W' of the last evaluated try
   DevBuf<double> ybuf_;    // Y' of the last loss-only try (n x ldx_), empty when PICARD_FLAG_NO_Y_STORE or out of memory
   bool ybuf_valid_ = false;
-  DevBuf<uint8_t> xs8_, wblob8_;  // sliced INT8 image of x1 (built at the first LOSS pass) and of the trial W (i8_loss.cu)
-  bool i8_failed_ = false;
+  // INT8 tensor-core passes (i8_loss.cu, i8_grad.cu): decided once per solver at the first LOSS pass (i8_prepare)
+  DevBuf<uint8_t> xs8_, wblob8_;  // digit image of x1 and of the trial W
+  DevBuf<double> xstats_;         // statistics of x1 gathered while slicing (I8_XSTATS)
+  DevBuf<int> rowexp_;            // exponents of the rows of the stored Y (gradient pass)
+  int i8_state_ = 0;              // 0 = undecided, 1 = in use, -1 = not used
+  bool i8_prepare();
   DevBuf<CoreScalars> sc_dev_;
   PinnedBuf<CoreScalars> sc_host_;
   // views into store_

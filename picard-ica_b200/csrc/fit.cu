@@ -458,6 +458,8 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   stats.kernel_launches += cs.kernel_launches;
   stats.pass_ms_fused = cs.pass_ms_fused; stats.pass_ms_grad = cs.pass_ms_grad; stats.pass_ms_loss = cs.pass_ms_loss;
   stats.grady_passes = cs.grady_passes; stats.pass_ms_grady = cs.pass_ms_grady;
+  stats.i8_loss_passes = cs.i8_loss_passes; stats.i8_grad_passes = cs.i8_grad_passes; stats.i8_fallbacks = cs.i8_fallbacks;
+  stats.i8_range = cs.i8_range;
   double* host_sources = nullptr;
   prefault.join();
   if (d_sources) {

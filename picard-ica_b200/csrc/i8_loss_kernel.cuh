@@ -1,0 +1,368 @@
+// =====================================================================================================
+// i8_loss_kernel.cuh -- the LOSS pass (Y' = W' x1, log-likelihood / y^2 row sums, Y' kept in HBM: core.rs:124-127 with
+// compute_loss core.rs:39-85) on the INT8 tensor cores: tcgen05.mma kind::i8, level accumulators in TMEM, the operands split
+// into balanced radix-256 digits (i8_common.cuh: S = 6 digits, 21 slice products, exact s32 level sums).
+//
+// x1 is fixed for a whole fit, so it is sliced ONCE (slice_x_kernel) into tiles of NT samples, each tile already in the shared-
+// memory image the tensor core reads (K-major rows of 128 bytes = the 128 components of a sample, SWIZZLE_128B pattern), one
+// [NT x 128 B] block per digit, followed by the NT sample exponents: a tile is one contiguous bulk copy (cp.async.bulk, no
+// tensor map).  W' (128 x 128) is sliced per try by a one-CTA kernel (slice_w_kernel).
+//
+// loss_i8_kernel, one CTA per SM, 18 warps:
+//   warp 16 (one lane) : bulk copies of the x1 tiles into a 2-stage ring (mbarrier transaction bytes)
+//   warp 17 (one lane) : per tile 21 products x 4 K-steps = 84 tcgen05.mma (128 x NT x 32, kind::i8).  The A operand (the W'
+//                        digits, 6 x 32 columns) lives in TENSOR MEMORY next to the 6 level accumulators (6 x NT columns), so
+//                        the MMAs only read the B operand from shared memory; tcgen05.commit releases the ring stage and
+//                        publishes the accumulators
+//   warps 0-15         : epilogue, thread = (row = TMEM lane, NT / 4 samples): tcgen05.ld of the 6 levels, accumulators returned
+//                        at once, exact 64-bit combination, scaling by exponent adds, log-likelihood (density.cuh), row sums per
+//                        thread; Y' through shared memory and TMA stores of [128 rows x 16 samples] boxes (the unit clips the
+//                        ragged last tile and the rows >= n_out); warps 0-3 first store W' into tensor memory
+// ABL (ablation bits, profiles/lab only; the library instantiates ABL = 0): 1 = no density, 2 = no Y' store, 4 = trace.
+// =====================================================================================================
+#pragma once
+#include "i8.cuh"
+#include "i8_common.cuh"
+
+namespace picard {
+namespace i8 {
+
+constexpr int KP = 128;                  // padded contraction length = bytes per operand row
+constexpr int SLICE_A_BYTES = 128 * KP;  // one digit of W': 128 rows x 128 bytes, plain row-major
+constexpr int W_EXP_OFFSET = S * SLICE_A_BYTES;
+static_assert(W_EXP_OFFSET + 128 * 4 == I8_WBLOB_BYTES, "wblob layout");
+
+template <int NT>
+struct LossGeom {
+  static_assert(NT % 16 == 0 && NT >= 16 && NT <= 64, "tile = a multiple of the 16-sample TMA store box and of the UMMA N step");
+  static constexpr int SLICE_B_BYTES = NT * KP;                    // one digit of a tile: NT samples x 128 bytes
+  static constexpr int TILE_BYTES = S * SLICE_B_BYTES + NT * 4;    // + the NT sample exponents (int)
+  static constexpr int STAGE_BYTES = ((TILE_BYTES + 1023) / 1024) * 1024;
+  static constexpr int NSTAGE = 2;
+  static constexpr int ACC_COLS = S * NT;                          // TMEM columns of the level accumulators of one tile
+  static constexpr int TMEM_A = ACC_COLS;                          // W' digit p, K-step k at column TMEM_A + 8 (4 p + k)
+  static_assert(ACC_COLS + S * 32 <= 512, "tensor memory: 512 columns");
+  static constexpr int NEW = 16;                                   // epilogue warps: TMEM lane quarter (warp & 3) x column quarter (warp >> 2)
+  static constexpr int CPT = NT / 4;                               // samples per epilogue thread and tile
+  static_assert(CPT % 4 == 0, "tcgen05.ld x4 / x8 granularity");
+  static constexpr int NTHREADS = 32 * (NEW + 2);
+  static constexpr int NBOX = NT / 16;                             // TMA store boxes per tile
+  static constexpr size_t SMEM_Y = (size_t)2 * 128 * NT * 8;       // Y' tile, two buffers of NBOX [128 rows][16 samples] SWIZZLE_128B boxes
+  static constexpr size_t SMEM_B = (size_t)NSTAGE * STAGE_BYTES;
+  static constexpr bool BIG = true;                                // density tables (80 KB)
+  static constexpr size_t SMEM_BYTES = SMEM_Y + SMEM_B + (size_t)dmath::Tab<BIG>::DOUBLES * 8 + 8192 /* sums */ + 256;
+  static constexpr uint32_t IDESC = make_idesc(NT);
+};
+
+// ---------------------------------------------------------------------------------------------------
+// slicing of x1: a CTA per tile of NT samples (grid-stride), thread = (sample r, 16-byte chunk ch of its 128 digit bytes).
+// Also gathers the statistics the range guard and the gradient pass need (I8_XSTATS).
+// ---------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(8 * NT) slice_x_kernel(const double* __restrict__ x, int64_t ldx, int64_t t_local, int n, int64_t n_tiles,
+                                                         uint8_t* __restrict__ blob, double* __restrict__ stats) {
+  using G = LossGeom<NT>;
+  __shared__ double red[8 * NT / 32][128];
+  const int tid = threadIdx.x, r = tid >> 3, ch = tid & 7, warp = tid >> 5, lane = tid & 31;
+  double rs[16];
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) rs[kk] = 0.0;
+  double sum_scale = 0.0, max_n2 = 0.0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t t = tile * NT + r;
+    double v[16];
+    double m = 0.0, n2 = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const int k = 16 * ch + kk;
+      v[kk] = (k < n && t < t_local) ? x[(size_t)k * ldx + t] : 0.0;
+      m = fmax(m, fabs(v[kk]));
+      n2 = fma(v[kk], v[kk], n2);
+      rs[kk] = fma(v[kk], v[kk], rs[kk]);
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    }
+    const int e = bound_exponent(m);
+    if (ch == 0 && t < t_local) {
+      sum_scale += scalbn(1.0, e - 1);
+      max_n2 = fmax(max_n2, n2);
+    }
+    uint64_t dg[16];
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) dg[kk] = split_digits(v[kk], e);
+    uint8_t* tb = blob + (size_t)tile * G::TILE_BYTES;
+#pragma unroll
+    for (int p = 0; p < S; ++p) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) w[kk >> 2] |= (uint32_t)((dg[kk] >> (8 * (S - 1 - p))) & 0xFF) << (8 * (kk & 3));
+      *reinterpret_cast<uint4*>(tb + (size_t)p * G::SLICE_B_BYTES + r * KP + ((ch ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (ch == 0) reinterpret_cast<int*>(tb + (size_t)S * G::SLICE_B_BYTES)[r] = e;
+  }
+  // statistics: row sums of squares over this CTA's samples (threads of equal ch hold the same 16 rows), scale sum, max norm
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) {
+    rs[kk] += __shfl_xor_sync(0xffffffffu, rs[kk], 8);
+    rs[kk] += __shfl_xor_sync(0xffffffffu, rs[kk], 16);
+  }
+#pragma unroll
+  for (int o = 8; o < 32; o <<= 1) {
+    sum_scale += __shfl_xor_sync(0xffffffffu, sum_scale, o);
+    max_n2 = fmax(max_n2, __shfl_xor_sync(0xffffffffu, max_n2, o));
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) red[warp][16 * lane + kk] = rs[kk];
+  }
+  if (lane == 0) {
+    atomicAdd(&stats[0], sum_scale);
+    atomicMax(reinterpret_cast<unsigned long long*>(&stats[1]), (unsigned long long)__double_as_longlong(max_n2));
+  }
+  __syncthreads();
+  if (tid < 128) {
+    double s = 0.0;
+    for (int w = 0; w < 8 * NT / 32; ++w) s += red[w][tid];
+    atomicAdd(&stats[2 + tid], s);
+  }
+}
+
+// slicing of W' (n_out x n_in, zero-padded to 128 x 128): one CTA, thread = (row, chunk); plain row-major digits (they go to
+// tensor memory row by row); the row exponents already carry COMBINE_EXP
+__global__ void __launch_bounds__(1024) slice_w_kernel(const double* __restrict__ w, int ldw, int n_out, int n_in, uint8_t* __restrict__ wblob) {
+  const int tid = threadIdx.x, r = tid >> 3, ch = tid & 7;
+  double v[16];
+  double m = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) {
+    const int k = 16 * ch + kk;
+    v[kk] = (r < n_out && k < n_in) ? w[(size_t)r * ldw + k] : 0.0;
+    m = fmax(m, fabs(v[kk]));
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const int e = bound_exponent(m);
+  uint64_t dg[16];
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) dg[kk] = split_digits(v[kk], e);
+#pragma unroll
+  for (int p = 0; p < S; ++p) {
+    uint32_t q4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) q4[kk >> 2] |= (uint32_t)((dg[kk] >> (8 * (S - 1 - p))) & 0xFF) << (8 * (kk & 3));
+    *reinterpret_cast<uint4*>(wblob + (size_t)p * SLICE_A_BYTES + r * KP + (ch << 4)) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+  }
+  if (ch == 0) reinterpret_cast<int*>(wblob + W_EXP_OFFSET)[r] = e + COMBINE_EXP;
+}
+
+#ifndef I8_TRACE_SLOTS
+#define I8_TRACE_SLOTS 0
+#endif
+
+// ---------------------------------------------------------------------------------------------------
+// the pass
+// ---------------------------------------------------------------------------------------------------
+template <int DENS, bool WANT_SQ, int NT, int ABL = 0>
+__global__ void __launch_bounds__(LossGeom<NT>::NTHREADS, 1)
+loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wblob, const __grid_constant__ CUtensorMap tmap_out,
+               const PassParams p, long long* __restrict__ trace) {
+  using G = LossGeom<NT>;
+  constexpr int NEW = G::NEW, CPT = G::CPT, NSTAGE = G::NSTAGE;
+  constexpr bool BIG = G::BIG;
+  constexpr bool NO_DENS = (ABL & 1) != 0, NO_STORE = (ABL & 2) != 0, TRACE = (ABL & 4) != 0;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  double* ysm = reinterpret_cast<double*>(smem);
+  unsigned char* sb = smem + G::SMEM_Y;
+  double* tab = reinterpret_cast<double*>(smem + G::SMEM_Y + G::SMEM_B);
+  double* sums = tab + dmath::Tab<BIG>::DOUBLES;  // [NEW / 4 - 1][2][128]: partial row sums of the column quarters
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sums + 1024);
+  uint64_t* a_full = bars;                 // W' digits stored in tensor memory (4 warps)
+  uint64_t* b_full = bars + 1;             // [NSTAGE] tile landed (transaction bytes)
+  uint64_t* b_empty = b_full + NSTAGE;     // [NSTAGE] MMA commit + the NEW epilogue warps (they read the sample exponents)
+  uint64_t* acc_full = b_empty + NSTAGE;   // accumulators of a tile complete (MMA commit)
+  uint64_t* acc_empty = acc_full + 1;      // accumulators read back (NEW epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr bool NEED_TAB = !NO_DENS && (DENS == DENS_TANH || DENS == DENS_EXP);
+  if (NEED_TAB) load_density_tables<BIG>(tab, DENS == DENS_TANH, tid, G::NTHREADS);
+  if (tid == 0) {
+    ptx::mbar_init(a_full, 4);
+    for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1 + NEW); }
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_empty, NEW);
+    ptx::fence_barrier_init();
+  }
+  if (warp == NEW + 1) tmem_alloc512(tmem_slot);  // the MMA warp owns the tensor memory: all 512 columns (one CTA per SM)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int64_t tile0 = blockIdx.x, tstride = gridDim.x;
+  const int64_t my_tiles = tile0 < p.n_tiles ? (p.n_tiles - tile0 + tstride - 1) / tstride : 0;
+
+  if (warp == NEW) {
+    // =================================== producer ===================================
+    if (lane == 0) {
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int st = (int)(it % NSTAGE);
+        ptx::mbar_wait(&b_empty[st], (uint32_t)(((it / NSTAGE) & 1) ^ 1));  // first round: passes on the fresh barrier
+        ptx::mbar_expect_tx(&b_full[st], (uint32_t)G::TILE_BYTES);
+        bulk_load(sb + (size_t)st * G::STAGE_BYTES, xblob + (size_t)(tile0 + it * tstride) * G::TILE_BYTES, G::TILE_BYTES, &b_full[st]);
+      }
+    }
+  } else if (warp == NEW + 1) {
+    // =================================== MMA issue ===================================
+    if (lane == 0) {
+      ptx::mbar_wait(a_full, 0);
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int st = (int)(it % NSTAGE);
+        if (TRACE && blockIdx.x == 0 && it < I8_TRACE_SLOTS) trace[it * 8 + 0] = clock64();
+        ptx::mbar_wait(&b_full[st], (uint32_t)((it / NSTAGE) & 1));
+        if (TRACE && blockIdx.x == 0 && it < I8_TRACE_SLOTS) trace[it * 8 + 1] = clock64();
+        const uint64_t db0 = make_desc(smem_u32(sb + (size_t)st * G::STAGE_BYTES));
+        ptx::mbar_wait(acc_empty, (uint32_t)((it & 1) ^ 1));  // the epilogue has read tile it - 1 back (first tile: passes)
+        tc_fence_after();
+        if (TRACE && blockIdx.x == 0 && it < I8_TRACE_SLOTS) trace[it * 8 + 2] = clock64();
+#pragma unroll
+        for (int d = 0; d < S; ++d) {
+          const uint32_t tacc = tmem + (uint32_t)(d * NT);
+#pragma unroll
+          for (int pa = 0; pa <= d; ++pa) {
+            const int qb = d - pa;
+#pragma unroll
+            for (int k = 0; k < KP / 32; ++k)
+              umma_i8_ts(tacc, tmem + (uint32_t)(G::TMEM_A + 8 * (4 * pa + k)), db0 + (uint64_t)((qb * G::SLICE_B_BYTES + k * 32) >> 4), G::IDESC,
+                         (pa > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&b_empty[st]);  // the ring stage may be refilled once these MMAs have read it (and the epilogue its exponents)
+        umma_commit(acc_full);      // the accumulators are complete
+        if (TRACE && blockIdx.x == 0 && it < I8_TRACE_SLOTS) trace[it * 8 + 3] = clock64();
+      }
+    }
+  } else {
+    // =================================== epilogue ===================================
+    const int q4 = warp & 3, cq = warp >> 2;   // TMEM lane quarter of this warp, column quarter of the tile
+    const int row = 32 * q4 + lane;
+    double sl = 0.0, sq = 0.0;
+    if (cq == 0) {  // warps 0-3: this thread's row of every W' digit into tensor memory (4 K-steps of 32 bytes = 8 columns each)
+#pragma unroll 1
+      for (int pa = 0; pa < S; ++pa) {
+        const uint4* src = reinterpret_cast<const uint4*>(wblob + (size_t)pa * SLICE_A_BYTES + (size_t)row * KP);
+#pragma unroll
+        for (int k = 0; k < KP / 32; ++k) {
+          const uint4 u0 = src[2 * k], u1 = src[2 * k + 1];
+          const uint32_t v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+          tmem_st8(tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(G::TMEM_A + 8 * (4 * pa + k)), v);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+    }
+    const int rexp = reinterpret_cast<const int*>(wblob + W_EXP_OFFSET)[row];  // row exponent + COMBINE_EXP
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int st = (int)(it % NSTAGE);
+      const int64_t t0 = (tile0 + it * tstride) * NT + CPT * cq;
+      const bool tr = TRACE && blockIdx.x == 0 && it < I8_TRACE_SLOTS && warp == 0 && lane == 0;
+      if (tr) trace[it * 8 + 4] = clock64();
+      // the level accumulators of this thread's samples; then the accumulators go back to the MMA warp
+      int32_t c[S][CPT];
+      const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(CPT * cq);
+      ptx::mbar_wait(acc_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      if (tr) trace[it * 8 + 5] = clock64();
+#pragma unroll
+      for (int d = 0; d < S; ++d) {
+#pragma unroll
+        for (int o = 0; o + 8 <= CPT; o += 8) tmem_ld8(taddr + (uint32_t)(d * NT + o), &c[d][o]);
+        if (CPT % 8 == 4) tmem_ld4(taddr + (uint32_t)(d * NT + CPT - 4), &c[d][CPT - 4]);
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      if (tr) trace[it * 8 + 6] = clock64();
+      double y[CPT];
+#pragma unroll
+      for (int e = 0; e < CPT; ++e) y[e] = combine_levels(c[0][e], c[1][e], c[2][e], c[3][e], c[4][e], c[5][e]);
+      // exponents of this thread's samples (bulk-copied with the tile: wait on its barrier for visibility; complete long ago),
+      // then the ring stage goes back to the producer
+      ptx::mbar_wait(&b_full[st], (uint32_t)((it / NSTAGE) & 1));
+      {
+        const int* csm = reinterpret_cast<const int*>(sb + (size_t)st * G::STAGE_BYTES + (size_t)S * G::SLICE_B_BYTES) + CPT * cq;
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) y[e] = scale_pow2(y[e], rexp + csm[e]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_empty[st]);
+      // log-likelihood / y^2 row sums
+      if (!NO_DENS) {
+        const bool partial_tile = (t0 + CPT > p.t_local);
+        if (!partial_tile) {
+#pragma unroll
+          for (int e = 0; e < CPT; ++e) {
+            double f = 0.0, fd = 0.0, dsd = 0.0;
+            density_eval<DENS, false, true, BIG>(y[e], p.dp, tab, f, fd, dsd, sl);
+            if (WANT_SQ) sq = fma(y[e], y[e], sq);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < CPT; ++e) {
+            double f = 0.0, fd = 0.0, dsd = 0.0, dl = 0.0;
+            density_eval<DENS, false, true, BIG>(y[e], p.dp, tab, f, fd, dsd, dl);
+            if (t0 + e < p.t_local) {
+              sl += dl;
+              if (WANT_SQ) sq = fma(y[e], y[e], sq);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) sl += y[e];
+      }
+      // Y' leaves through shared memory and the TMA unit (a thread's samples are CPT * 8 bytes of ITS row: direct stores would be
+      // 32 different lines per instruction).  Box = 16 samples x 128 rows, SWIZZLE_128B; the unit clips the ragged last tile
+      // and the rows >= n_out.  The buffer of tile it - 2 is free: thread 0 waited for its store group before the last barrier.
+      if (!NO_STORE && p.out != nullptr) {
+        double* yb = ysm + (size_t)(it & 1) * 128 * NT + row * 16;
+#pragma unroll
+        for (int e = 0; e < CPT; e += 2) {
+          const int col = CPT * cq + e;  // sample within the tile: box col >> 4, 16-byte chunk (col & 15) >> 1 of the box row
+          *reinterpret_cast<double2*>(yb + (size_t)(col >> 4) * 128 * 16 + ((((col & 15) >> 1) ^ (row & 7)) << 1)) = make_double2(y[e], y[e + 1]);
+        }
+        ptx::fence_proxy_async();
+        if (tid == 0) bulk_wait_read0();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");
+        if (tid == 0) {
+          const int64_t tt = (tile0 + it * tstride) * NT;
+#pragma unroll
+          for (int b = 0; b < G::NBOX; ++b) tma_store_2d(&tmap_out, ysm + (size_t)(it & 1) * 128 * NT + (size_t)b * 128 * 16, (int)(tt + 16 * b), 0);
+          bulk_commit();
+        }
+      }
+      if (tr) trace[it * 8 + 7] = clock64();
+    }
+    if (!NO_STORE && p.out != nullptr && tid == 0) bulk_wait0();
+    // the column quarters of a row live in warps q4, q4 + 4, q4 + 8, q4 + 12
+    if (cq > 0) { sums[(cq - 1) * 256 + row] = sl; sums[(cq - 1) * 256 + 128 + row] = sq; }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");
+    if (cq == 0) {
+      for (int o = 0; o < NEW / 4 - 1; ++o) { sl += sums[o * 256 + row]; sq += sums[o * 256 + 128 + row]; }
+      double* out = p.partial + (size_t)blockIdx.x * (3 * 128);  // [Sd (unused) | Sq | L] of the 128 rows: rb_partial_size(128, 128, false, false)
+      out[row] = 0.0; out[128 + row] = sq; out[256 + row] = sl;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NEW + 1) tmem_dealloc512(tmem);
+}
+
+}  // namespace i8
+}  // namespace picard

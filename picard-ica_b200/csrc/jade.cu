@@ -278,11 +278,11 @@ template <int NP>
 int launch_cumulants(const double* d_x, int n, int64_t t_local, int64_t ld, int sm_count, cudaStream_t st, double* d_partial, int& n_tg,
                      int& pairs_padded) {
   using G = JadeGeom<NP>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceInt configured;
+  configured.get([&] {
     PICARD_CUDA(cudaFuncSetAttribute(jade_cumulant_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
-    configured = true;
-  }
+    return 1;
+  });
   const int n_pairs = n * (n + 1) / 2;
   const int n_pg = (n_pairs + G::PPC - 1) / G::PPC;
   const int64_t n_tiles = (t_local + G::BT - 1) / G::BT;

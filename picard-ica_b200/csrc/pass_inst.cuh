@@ -9,14 +9,14 @@ template <int NP, int DENS, int MODE, bool WANT_H>
 static int launch_one(const PassLaunch& L, const CUtensorMap& tmap) {
   using G = PassGeom<NP>;
   auto kern = pass_kernel<NP, DENS, MODE, WANT_H>;
-  static int blocks_per_sm = 0;  // per instantiation
-  if (blocks_per_sm == 0) {
+  static PerDeviceInt cache;  // per instantiation and per device
+  const int blocks_per_sm = cache.get([&] {
     PICARD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
     int b = 0;
     PICARD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, G::NTHREADS, G::SMEM_BYTES));
     if (b < 1) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: pass kernel does not fit on this device");
-    blocks_per_sm = b > PASS_MAX_BLOCKS_PER_SM ? PASS_MAX_BLOCKS_PER_SM : b;
-  }
+    return b > PASS_MAX_BLOCKS_PER_SM ? PASS_MAX_BLOCKS_PER_SM : b;
+  });
   const int64_t n_tiles = (L.t_local + G::BT - 1) / G::BT;
   int64_t grid = (int64_t)L.sm_count * blocks_per_sm;
   if (grid > n_tiles) grid = n_tiles;

@@ -30,18 +30,6 @@
 
 namespace picard {
 
-#ifdef PICARD_RB_TRACE
-// Debug build only (profiles/rb_trace.sh): clock64() at the phase boundaries of every warp of CTA 0 for the first tiles.
-constexpr int RB_TRACE_TILES = 96;
-static __device__ long long g_rb_trace[16 * RB_TRACE_TILES * 8];
-#define RB_TRACE(slot)                                                                                         \
-  do {                                                                                                         \
-    if (blockIdx.x == 0 && lane == 0 && it < RB_TRACE_TILES) g_rb_trace[(warp * RB_TRACE_TILES + (int)it) * 8 + (slot)] = clock64(); \
-  } while (0)
-#else
-#define RB_TRACE(slot) do { } while (0)
-#endif
-
 __host__ __device__ inline int rb_partial_size(int rp, int np, bool want_g, bool want_h) {
   return (want_g ? rp * np : 0) + (want_h ? rp * np : 0) + 3 * rp;
 }
@@ -96,13 +84,8 @@ static __global__ void reduce_rb_kernel(const double* __restrict__ partial, int 
 template <int KP>
 struct RbLossGeom {
   static_assert(KP == 64 || KP == 128 || KP == 256, "register-resident A fragments are sized for KP = 64, 128 or 256");
-#ifdef PICARD_RB_LOSS_W16  // A/B build (profiles/rb_variant.sh): KP = 128 with 16 warps x 8 rows instead of 8 warps x 16 rows; measured 10.95 vs 10.85 ms
-  static constexpr int NWARPS = KP == 128 ? 16 : 8;
-  static constexpr int MB = 1;
-#else
   static constexpr int NWARPS = 8;
   static constexpr int MB = KP == 128 ? 2 : 1;   // 8-row blocks per warp: MB * KP / 4 = 64 A-fragment doubles per thread
-#endif
   static constexpr int NTHREADS = NWARPS * 32;
   static constexpr int RP = 8 * MB * NWARPS;     // rows of Y' per CTA
   static constexpr int KS = KP / 4;              // k-steps
@@ -177,9 +160,7 @@ rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, con
     const int64_t t0 = (tile0 + it * tstride) * G::BT;
     const bool partial_tile = (t0 + G::BT > p.t_local);
     const double* xst = xs + stage * KP * G::BT;
-    RB_TRACE(0);
     ptx::mbar_wait(&bar[stage], parity);
-    RB_TRACE(1);
 
     double acc[MB][2][2];
 #pragma unroll
@@ -202,8 +183,6 @@ rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, con
         ptx::tma_load_2d(xs + stage * KP * G::BT, &tmap, (int)((tile0 + (it + G::STAGES) * tstride) * G::BT), 0, &bar[stage]);
       }
     });
-
-    RB_TRACE(2);
     // acc[mb][nb][pp] <-> row 8 (MB warp + mb) + c, sample 2 (2 j + pp) + nb.
     // Two instantiations of the epilogue: interior tiles (every sample valid: no per-element bounds logic -- the epilogue is
     // issue-bound, and every instruction saved shortens the time both warps of a scheduler spend off the DMMA pipe) and the
@@ -257,7 +236,6 @@ rb_loss_kernel(const __grid_constant__ CUtensorMap tmap, const PassParams p, con
     };
     if (!partial_tile) epilogue(std::true_type{});
     else epilogue(std::false_type{});
-    RB_TRACE(3);
   }
 
   if (!APPLY) {

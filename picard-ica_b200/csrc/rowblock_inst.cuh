@@ -1,6 +1,6 @@
 // Launchers of the row-block kernels (rowblock.cuh); one translation unit per padded size (rb_np*.cu).
 #pragma once
-#include "rowblock_ws.cuh"
+#include "rowblock.cuh"
 
 namespace picard {
 
@@ -27,8 +27,8 @@ template <int KP, int DENS, int MODE, bool WANT_SQ>
 static int launch_rb_loss_one(const PassLaunch& L, const CUtensorMap& tmap) {
   using G = RbLossGeom<KP>;
   auto kern = rb_loss_kernel<KP, DENS, MODE, WANT_SQ>;
-  static int bps = 0;
-  if (bps == 0) bps = rb_blocks_per_sm(kern, G::NTHREADS, G::SMEM_BYTES);
+  static PerDeviceInt cache;  // per instantiation and per device
+  const int bps = cache.get([&] { return rb_blocks_per_sm(kern, G::NTHREADS, G::SMEM_BYTES); });
   const int64_t n_tiles = (L.t_local + G::BT - 1) / G::BT;
   const int nrb = (L.n_out + G::RP - 1) / G::RP;
   int64_t n_tg = ((int64_t)L.sm_count * bps) / nrb;
@@ -45,57 +45,14 @@ static int launch_rb_loss_one(const PassLaunch& L, const CUtensorMap& tmap) {
   return launches;
 }
 
-// PICARD_RB_WS=1 selects the warp-specialised LOSS / APPLY kernel of rowblock_ws.cuh (an experiment kept for A/B
-// measurements: parity-green, but measured SLOWER than the unspecialised kernel -- see the header of rowblock_ws.cuh)
-static inline bool rb_use_ws() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PICARD_RB_WS");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
-}
-
-template <int KP, int DENS, int MODE, bool WANT_SQ>
-static int launch_rb_loss_ws_one(const PassLaunch& L, const CUtensorMap& tmap) {
-  using G = RbLossWsGeom<KP>;
-  auto kern = rb_loss_ws_kernel<KP, DENS, MODE, WANT_SQ>;
-  static int bps = 0;
-  if (bps == 0) bps = rb_blocks_per_sm(kern, G::NTHREADS, G::SMEM_BYTES);
-  const int64_t n_tiles = (L.t_local + G::BT - 1) / G::BT;
-  const int nrb = (L.n_out + G::RP - 1) / G::RP;
-  int64_t n_tg = ((int64_t)L.sm_count * bps) / nrb;
-  if (n_tg > n_tiles) n_tg = n_tiles;
-  if (n_tg < 1) n_tg = 1;
-  PassParams p;
-  p.w = L.d_w; p.bias = L.d_bias; p.n_out = L.n_out; p.n_in = L.n_in; p.ldw = L.ldw;
-  p.t_local = L.t_local; p.n_tiles = n_tiles; p.dp = make_dens_params(DENS, L.alpha);
-  p.partial = L.d_partial; p.out = L.d_out; p.ld_out = L.ld_out;
-  // Y' leaves through the TMA unit: box = 16 samples x RP rows of the output, clipped at t_local and n_out
-  const CUtensorMap tmap_out = L.d_out != nullptr ? make_tmap(L.d_out, L.ld_out, L.t_local, L.n_out, G::RP) : tmap;
-  kern<<<(unsigned)(n_tg * nrb), G::NTHREADS, G::SMEM_BYTES, L.stream>>>(tmap, tmap_out, p, nrb);
-  PICARD_CUDA(cudaGetLastError());
-  int launches = 1;
-  if (MODE != PASS_APPLY) launches += rb_reduce(L, (int)n_tg, nrb, G::RP, KP, false, false, true);
-  return launches;
-}
-
-template <int KP, int DENS, int MODE, bool WANT_SQ>
-static int launch_rb_loss_any(const PassLaunch& L, const CUtensorMap& tmap) {
-  if constexpr (KP >= 128) {
-    if (rb_use_ws()) return launch_rb_loss_ws_one<KP, DENS, MODE, WANT_SQ>(L, tmap);
-  }
-  return launch_rb_loss_one<KP, DENS, MODE, WANT_SQ>(L, tmap);
-}
-
 template <int KP, int DENS>
 static int launch_rb_loss_dens(const PassLaunch& L, const CUtensorMap& tmap) {
-  return L.want_h ? launch_rb_loss_any<KP, DENS, PASS_LOSS, true>(L, tmap) : launch_rb_loss_any<KP, DENS, PASS_LOSS, false>(L, tmap);
+  return L.want_h ? launch_rb_loss_one<KP, DENS, PASS_LOSS, true>(L, tmap) : launch_rb_loss_one<KP, DENS, PASS_LOSS, false>(L, tmap);
 }
 
 template <int KP>
 int launch_rb_loss(const PassLaunch& L, const CUtensorMap& tmap) {
-  if (L.mode == PASS_APPLY) return launch_rb_loss_any<KP, DENS_LINEAR, PASS_APPLY, false>(L, tmap);
+  if (L.mode == PASS_APPLY) return launch_rb_loss_one<KP, DENS_LINEAR, PASS_APPLY, false>(L, tmap);
   switch (L.dens) {
     case DENS_TANH: return launch_rb_loss_dens<KP, DENS_TANH>(L, tmap);
     case DENS_EXP: return launch_rb_loss_dens<KP, DENS_EXP>(L, tmap);
@@ -109,8 +66,8 @@ template <int NP, int DENS, bool WANT_H, bool HAS_BIAS>
 static int launch_rb_grady_one(const PassLaunch& L, const CUtensorMap& tmap) {
   using G = RbGradYGeom<NP, WANT_H>;
   auto kern = rb_grady_kernel<NP, DENS, WANT_H, HAS_BIAS>;
-  static int bps = 0;
-  if (bps == 0) bps = rb_blocks_per_sm(kern, G::NTHREADS, G::SMEM_BYTES);
+  static PerDeviceInt cache;  // per instantiation and per device
+  const int bps = cache.get([&] { return rb_blocks_per_sm(kern, G::NTHREADS, G::SMEM_BYTES); });
   const int64_t n_tiles = (L.t_local + G::BT - 1) / G::BT;
   const int nrb = (L.n_out + G::RP - 1) / G::RP;
   int64_t n_tg = ((int64_t)L.sm_count * bps) / nrb;

@@ -1034,12 +1034,12 @@ int matrix_exp(const double* D, double alpha, double norm_d, int n, const ExpmWo
   if (grid > EXPM_MAX_CTAS) throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: matrix_exp supports n <= 256");
   int as_in_smem = n <= 128 ? 1 : 0;  // A_s (n x n) staged in shared memory when it fits
   const size_t smem = sizeof(double) * (3 * EXPM_ROWS * (size_t)(n + 4) + (as_in_smem ? (size_t)n * (n + 8) : 0));
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceInt configured;
+  configured.get([&] {
     PICARD_CUDA(cudaFuncSetAttribute(expm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(sizeof(double) * (3 * EXPM_ROWS * (128 + 4) + 128 * (128 + 8)))));
-    configured = true;
-  }
+    return 1;
+  });
   // w.slots: [barrier counter (8 doubles)][flags: 31 x grid doubles]; all-ones bytes = NaN = "not published yet"
   unsigned int* bar = reinterpret_cast<unsigned int*>(w.slots);
   double* flags = w.slots + 8;
@@ -1061,13 +1061,13 @@ int matrix_exp_candidates(const double* D, double alpha0, double norm_d, int n, 
   const int grid = (n + EXPM_ROWS - 1) / EXPM_ROWS;
   int as_in_smem = n <= 128 ? 1 : 0;
   const size_t smem = sizeof(double) * (2 * EXPM_ROWS * (size_t)(n + 4) + (as_in_smem ? (size_t)n * (n + 8) : 0));
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceInt configured;
+  configured.get([&] {
     const int mx = (int)(sizeof(double) * (2 * EXPM_ROWS * (128 + 4) + 128 * (128 + 8)));
     PICARD_CUDA(cudaFuncSetAttribute(expm_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     PICARD_CUDA(cudaFuncSetAttribute(expm_multi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    configured = true;
-  }
+    return 1;
+  });
   double* flags = w.slots + 8;
   PICARD_CUDA(cudaMemsetAsync(flags, 0xFF, sizeof(double) * 31 * (size_t)grid, st));
   void* args[] = {(void*)&D, (void*)&alpha0, (void*)&first_norm, (void*)&n, (void*)&n_cand, (void*)&flags, (void*)&W, (void*)&Wt_all,

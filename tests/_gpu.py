@@ -38,6 +38,21 @@ def eval_moments(x, w=None, kind=0, alpha=1.0, mode=0, want_h=True, device=0):
     return dict(gr=gr, sd=sd, hr=hr, sq=sq, lrow=lrow)
 
 
+def eval_moments_ex(x, w=None, kind=0, alpha=1.0, mode=0, want_h=True, flags=0, whitened=False, device=0):
+    """picard_eval_moments_ex -> (dict(gr, sd, hr, sq, lrow), stats dict): explicit PICARD_FLAG_* bits and the `whitened` promise."""
+    x = _c(x); w = _c(w); n, t = x.shape
+    gr = np.full((n, n), np.nan); hr = np.full((n, n), np.nan)
+    sd = np.full(n, np.nan); sq = np.full(n, np.nan); lrow = np.full(n, np.nan)
+    err = C.create_string_buffer(1024)
+    stats = _ffi.Stats()
+    st = _ffi.lib().picard_eval_moments_ex(_p(x), C.c_int64(n), C.c_int64(t), C.c_int64(x.strides[0] // 8), _p(w), C.c_int32(kind),
+                                           C.c_double(alpha), C.c_int32(mode), C.c_int32(int(want_h)), C.c_int32(device),
+                                           C.c_uint32(flags), C.c_int32(int(whitened)), _p(gr), _p(sd), _p(hr), _p(sq), _p(lrow),
+                                           C.byref(stats), err, C.c_size_t(1024))
+    _check(st, err)
+    return dict(gr=gr, sd=sd, hr=hr, sq=sq, lrow=lrow), stats.as_dict()
+
+
 def eval_point(x, w=None, kind=0, alpha=1.0, ortho=True, extended=True, lambda_min=0.01, c=None, old_signs=None, loss_signs=None,
                device=0):
     """picard_eval_point -> dict(g, h, hoff, signs, sign_change, gradient_norm, loss)."""

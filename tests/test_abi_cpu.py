@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_status_strings():
     lib = _ffi.lib()
-    assert lib.picard_abi_version() == 1
+    assert lib.picard_abi_version() == 2
     # Display texts of error.rs:44-74
     assert lib.picard_status_string(2).decode() == "Singular matrix encountered during computation"
     assert lib.picard_status_string(1).decode().startswith("Invalid dimensions")
@@ -41,8 +41,8 @@ def test_abi_version_and_status_strings():
 def test_struct_layouts_match_header_sizes():
     # natural alignment on x86-64: computed by hand from include/picard_b200.h
     assert C.sizeof(_ffi.Config) == 160
-    assert C.sizeof(_ffi.Stats) == 144
-    assert C.sizeof(_ffi.Result) == 88 + 144
+    assert C.sizeof(_ffi.Stats) == 176
+    assert C.sizeof(_ffi.Result) == 88 + 176
 
 
 def test_config_defaults():  # config.rs:64-85

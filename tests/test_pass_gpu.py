@@ -131,103 +131,3 @@ def test_large_values_saturate_cleanly():
     for k in ("gr", "sd", "sq", "lrow"):
         assert np.all(np.isfinite(got[k]))
         assert _data.rel_err(got[k], getattr(ref, k)) <= TOL
-
-
-_WS_SCRIPT = r"""
-import sys
-sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
-import numpy as np
-import _data, _gpu
-from oracle import oracle as orc
-for n, t, kind, alpha in [(128, 2050, orc.TANH, 1.0), (100, 1500, orc.TANH, 1.0), (256, 1040, orc.EXP, 0.1), (200, 2001, orc.TANH, 1.0)]:
-    x = _data.whitened(n, t, seed=n)
-    w = _data.orthogonal(n, seed=n + 2) + 0.02 * np.random.default_rng(n).standard_normal((n, n))
-    ref = orc.eval_point(x, w, kind, alpha, ortho=False, extended=False)
-    for want_h in (True, False):
-        got = _gpu.eval_moments(x, w, kind, alpha, mode=3, want_h=want_h)   # LOSS + Y store (TMA store), then gradient from the stored Y
-        for k in ("gr", "sd", "lrow") + (("hr", "sq") if want_h else ()):
-            e = _data.rel_err(got[k], getattr(ref, k))
-            assert e <= 1e-10, (n, t, k, e)
-print("ok")
-"""
-
-
-def test_warp_specialised_loss_kernel_is_parity_green():
-    """rowblock_ws.cuh (PICARD_RB_WS=1, an opt-in experiment): same raw moments as the oracle, ragged last tile and N < KP included.
-    The switch is read once per process, hence the subprocess."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PICARD_RB_WS="1")
-    r = subprocess.run([sys.executable, "-c", _WS_SCRIPT.format(root=root, tests=os.path.join(root, "tests"))], env=env, capture_output=True,
-                       text=True, timeout=300)
-    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
-
-
-_I8_SCRIPT = r"""
-import sys
-sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
-import numpy as np
-import _data, _gpu
-from oracle import oracle as orc
-for n, t, kind, alpha in [(128, 2050, orc.TANH, 1.0), (100, 1500, orc.TANH, 0.7), (65, 33, orc.TANH, 1.0), (128, 4097, orc.EXP, 0.1), (70, 4099, orc.CUBE, 1.0)]:
-    x = _data.whitened(max(n, 1), max(t, 2 * n), seed=n)[:, :t] if t < n else _data.whitened(n, t, seed=n)
-    w = _data.orthogonal(n, seed=n + 2) + 0.02 * np.random.default_rng(n).standard_normal((n, n))
-    ref = orc.eval_point(x, w, kind, alpha, ortho=False, extended=False)
-    got = _gpu.eval_moments(x, w, kind, alpha, mode=2, want_h=True)      # LOSS pass: log-likelihood and y^2 row sums
-    for k in ("lrow", "sq"):
-        e = _data.rel_err(got[k], getattr(ref, k))
-        assert e <= 1e-10, (n, t, k, e)
-    got = _gpu.eval_moments(x, w, kind, alpha, mode=3, want_h=False)     # gradient moments from the Y' the INT8 pass stored
-    for k in ("gr", "sd", "lrow"):
-        e = _data.rel_err(got[k], getattr(ref, k))
-        assert e <= 1e-10, (n, t, k, e)
-print("ok")
-"""
-
-
-def test_int8_tensor_core_loss_pass_matches_oracle():
-    """i8_loss.cu (tcgen05.mma kind::i8, error-free 7-slice splitting; PICARD_I8=1 forces it on the test hook, whose data is
-    not flagged as whitened): raw LOSS moments and the stored Y' against the oracle, ragged last tile, N < 128 padding, T < 32."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PICARD_I8="1")
-    r = subprocess.run([sys.executable, "-c", _I8_SCRIPT.format(root=root, tests=os.path.join(root, "tests"))], env=env, capture_output=True,
-                       text=True, timeout=300)
-    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
-
-
-def test_int8_and_fp64_loss_paths_give_the_same_fit():
-    """A whitened N = 100 fit takes the INT8 LOSS pass automatically; PICARD_I8=0 in a subprocess gives the FP64 path: same
-    iteration count, unmixing within Amari 1e-6 (BASELINE tolerance)."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    script = r"""
-import sys
-sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
-import numpy as np
-import _data
-import picard_ica_b200 as P
-x, a, _ = _data.mixture(100, 30000, seed=5, kind="mixed")
-w0 = _data.orthogonal(100, 43)
-res = P.Picard.fit_with_config(x, P.PicardConfig(w_init=w0, max_iter=60))
-np.save(sys.argv[1], res.full_unmixing())
-print(res.n_iterations)
-""".format(root=root, tests=os.path.join(root, "tests"))
-    outs = []
-    import tempfile
-    import numpy as np
-    import picard_ica_b200 as P
-    with tempfile.TemporaryDirectory() as td:
-        for mode in ("1", "0"):
-            f = os.path.join(td, f"w{mode}.npy")
-            r = subprocess.run([sys.executable, "-c", script, f], env=dict(os.environ, PICARD_I8=mode), capture_output=True, text=True, timeout=300)
-            assert r.returncode == 0, r.stdout + r.stderr
-            outs.append((int(r.stdout.strip().splitlines()[-1]), np.load(f)))
-    assert abs(outs[0][0] - outs[1][0]) <= 1
-    assert P.utils.amari_distance(outs[0][1], np.linalg.pinv(outs[1][1])) <= 1e-6

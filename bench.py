@@ -6,19 +6,25 @@ uniform sources mixed by a seed-42 N(0,1) matrix, explicit seed-43 orthogonal w_
 --gpus N the T samples are sharded over N ranks (strong scaling, one NCCL allreduce of the packed N x N
 moments per pass).
 
-A "step" is one outer Picard iteration (core.rs:211-391): gradient pass + line-search passes over the
-sample matrix + the N x N work between them.
+A "step" is one outer Picard iteration (core.rs:211-391): the stored-Y gradient pass + the LOSS passes of the
+line search over the sample matrix + the N x N work between them.
   value  : iterations/sec of the core loop with the preprocessed data resident in HBM (picard_core_run),
            device time from CUDA events recorded on the library's stream, max over ranks.
   e2e    : iterations/sec through the reference-facing call Picard.fit_with_config on HOST buffers (pinned):
            H2D of X, centering, whitening, the whole fit to convergence, D2H of the sources -- all timed.
-  roofline: the fused pass kernel (K1): algorithmic FP64 flops (4 N^2 T_local per launch)
-           / its mean launch duration (CUDA events inside the library around each pass launch).
+  roofline: the pass kernel with the largest share of the step (LOSS pass of a line-search try: 2 N^2 T_local f64
+           flops per launch; stored-Y gradient pass: 2 N^2 T_local, 4 N^2 T_local with the Hessian moments) against
+           the FP64 tensor (DMMA) peak measured by a microbenchmark at the start of THIS run (picard_fp64_peak_probe;
+           MEASURED_PEAKS.json has no FP64 entry); launch durations from CUDA events inside the library around each
+           pass launch.  For the INT8 tensor-core engines the `engine` sub-object gives the integer-op view.
+  parity : run beside the measurement -- the INT8 engines against the FP64 kernels on the full device-resident data
+           (LOSS moments + stored-Y gradient at one W), and a 1e5-sample slice against the CPU oracle.
   cpu_baseline: the CPU oracle (a restatement of the reference's cost structure, oracle/picard_oracle.cpp)
            timed on this box's host cores on a bounded sample (N=128, T=T_cpu) and scaled linearly in T.
 
 `--impl reference` times the CPU oracle as the reference arm (the Rust reference cannot be built in this
-image: no cargo/rustc).
+image: no cargo/rustc): a step is ONE outer iteration of the oracle's core loop on T = 1e6 samples
+(1/10 of the workload), iterations/s scaled linearly in T.
 """
 from __future__ import annotations
 
@@ -52,9 +58,10 @@ WORKLOADS = {
     "c5": dict(n=32, t=1_000_000, ortho=True, extended=True, kind=0, alpha=1.0, n_laplace=16, jade_it=50,
                desc="N=32,T=1e6 f64 jade_it=50 warm start then Picard-O extended (JADE runs inside the e2e fit)"),
 }
-I8_LOSS_TRAFFIC = 19.233e9  # dram bytes per launch of loss_i8_kernel at c3 from the ncu --set full capture (profiles/summary_r01i.txt)
-FP64_PEAK_TFLOPS = 37.19  # measured by us on this pool's B200 (profiles/microbench/fp64_pipes_r01.jsonl, DMMA m8n8k4);
-#                           MEASURED_PEAKS.json has no FP64 figure
+FP64_PEAK_FALLBACK_TFLOPS = 37.19  # round-1 microbenchmark (profiles/microbench/fp64_pipes_r01.jsonl); used only if the in-run probe fails
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at c3 on one GPU, from the committed ncu --set full captures (None = not
+# captured for the current kernel).  Scaled to the rank's share of the samples; reported with its source, never silently.
+NCU_TRAFFIC_C3 = {"loss": (None, None), "grady": (None, None)}
 
 
 class ClockSampler(threading.Thread):
@@ -138,8 +145,28 @@ def host_inputs(n):
     return a, w0
 
 
-def cpu_oracle_rate(wl, t_cpu, max_iter, threads=None):
-    """Iterations/sec of the CPU oracle core loop on a bounded sample, scaled linearly in T to the workload."""
+def config_dict(args, wl, world, t_total, t_local):
+    """The `config` object: identical in the b200 arm and the reference arm of the same launch."""
+    return {"workload": wl["desc"], "name": args.workload, "n": wl["n"], "t_total": int(t_total), "t_per_gpu": int(t_local),
+            "parallelism": f"sample-sharded x{world}",
+            "l2": "inputs (8*N*T_local bytes per pass) far exceed the 126 MB L2",
+            "timing": "b200 arm: CUDA events on the library stream around picard_core_run, max over ranks (wall clock cross-check in "
+                      "wall_ms_per_step); reference arm: wall clock of the CPU core loop on the bounded sample named in "
+                      "cpu_baseline.sample, iterations/s scaled linearly in T to t_total, rank 0 only"}
+
+
+def shard_sizes(wl, world):
+    from picard_ica_b200.dist import shard_range
+    t_total = wl["t"]
+    if "per_gpu_t" in wl and world * wl["per_gpu_t"] < t_total:
+        t_total = world * wl["per_gpu_t"]  # c4 is specified for 8 GPUs: keep its per-GPU shard when fewer are available
+    return t_total, shard_range(t_total, 0, world)
+
+
+def cpu_oracle_rate(wl, t_cpu, warm_iters, timed_iters, threads=None):
+    """Iterations/sec of the CPU oracle core loop (oracle/picard_oracle.cpp, the reference's cost structure on the same BLAS) on a
+    bounded sample: warm_iters untimed outer iterations, then timed_iters timed ones (both from W = I on the same whitened data);
+    scaled linearly in T to the workload."""
     import numpy as np
     import _data
     from oracle import oracle as orc
@@ -148,9 +175,11 @@ def cpu_oracle_rate(wl, t_cpu, max_iter, threads=None):
     n = wl["n"]
     kind = "mixed" if 0 < wl["n_laplace"] < n else ("laplace" if wl["n_laplace"] else "uniform")
     xw = _data.whitened(n, t_cpu, seed=42, kind=kind)
+    kw = dict(covariance=np.eye(n) if wl["extended"] else None, want_y=False)
+    if warm_iters > 0:
+        orc.core_run(xw, wl["kind"], wl["alpha"], wl["ortho"], wl["extended"], max_iter=warm_iters, **kw)
     t0 = time.perf_counter()
-    r = orc.core_run(xw, wl["kind"], wl["alpha"], wl["ortho"], wl["extended"], max_iter=max_iter,
-                     covariance=np.eye(n) if wl["extended"] else None, want_y=False)
+    r = orc.core_run(xw, wl["kind"], wl["alpha"], wl["ortho"], wl["extended"], max_iter=timed_iters, **kw)
     wall = time.perf_counter() - t0
     secs = r.seconds if r.seconds > 0 else wall
     it_s_sample = r.n_iterations / secs
@@ -159,29 +188,41 @@ def cpu_oracle_rate(wl, t_cpu, max_iter, threads=None):
                 cores=orc.get_threads(), loss_evals=r.loss_evals)
 
 
-def run_reference(args, wl, rank, out):
+def host_description():
+    try:
+        import psutil
+        ram = psutil.virtual_memory().total / 2 ** 30
+    except Exception:
+        ram = float("nan")
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"cpu": model, "logical_cores": os.cpu_count(), "ram_gib": round(ram, 1)}
+
+
+def run_reference(args, wl, rank, world, out):
+    """The reference arm: the reference's own CPU path (here: the C++ port of it, see the module docstring) on the host cores.
+    A step is ONE outer iteration of the core loop on T = --ref-t samples (default 1e6 = T/10)."""
     if rank != 0:
         return
     ncores = os.cpu_count() or 1
-    per_step = []
-    total_it, total_s = 0, 0.0
-    res = None
-    for i in range(args.warmup + args.steps):
-        res = cpu_oracle_rate(wl, args.cpu_t, args.cpu_iters, ncores)
-        if i >= args.warmup:
-            total_it += res["iters"]; total_s += res["seconds"]
-            per_step.append(res["seconds"])
-    value = (total_it / total_s) * (args.cpu_t / wl["t"])
-    sample = (f"oracle core loop, N={wl['n']}, T={args.cpu_t} (1/{wl['t'] // args.cpu_t} of the workload), {args.cpu_iters} outer "
-              f"iterations per step, iterations/s scaled linearly in T to T={wl['t']}")
+    t_total, (b0, e0) = shard_sizes(wl, world)
+    res = cpu_oracle_rate(wl, args.ref_t, args.warmup, args.steps, ncores)
+    value = res["value"]
+    sample = (f"oracle core loop (C++ port of core.rs on OpenBLAS, {res['cores']} threads), N={wl['n']}, T={args.ref_t} "
+              f"(1/{wl['t'] / args.ref_t:g} of the workload): {args.warmup} warm-up + {res['iters']} timed outer iterations in "
+              f"{res['seconds']:.1f} s ({res['it_s_sample']:.4f} it/s on the sample), iterations/s scaled linearly in T to T={wl['t']}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(len(per_step), 1), "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / max(res["iters"], 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload, "n": wl["n"], "t_total": wl["t"], "t_per_gpu": wl["t"],
-                   "parallelism": "host CPU, all cores (OpenBLAS threads); reference arm runs on rank 0 only",
-                   "l2": "n/a (CPU)", "timing": "wall clock of the oracle core loop on the bounded sample, scaled linearly in T"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": sample},
+        "config": config_dict(args, wl, world, t_total, e0 - b0),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": sample, "host": host_description()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -206,11 +247,13 @@ def _main(out):
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-t", type=int, default=100_000, help="samples of the CPU-baseline sample")
-    ap.add_argument("--cpu-iters", type=int, default=6, help="outer iterations of the CPU-baseline sample")
+    ap.add_argument("--cpu-t", type=int, default=1_000_000, help="samples of the cpu_baseline sample of the b200 arm (T/10)")
+    ap.add_argument("--cpu-iters", type=int, default=2, help="timed outer iterations of the cpu_baseline sample (after one warm-up iteration)")
+    ap.add_argument("--ref-t", type=int, default=1_000_000, help="samples of the reference arm's bounded sample (T/10, SURVEY.md §8d)")
     ap.add_argument("--flags", type=int, default=0, help="PICARD_FLAG_* bits (ablation)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -218,7 +261,7 @@ def _main(out):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, wl, rank, out)
+        run_reference(args, wl, rank, world, out)
         return
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
@@ -301,6 +344,14 @@ def _main(out):
         return restarts
 
     run_iters(args.warmup)
+    # FP64 tensor (DMMA) peak of THIS device at its current clocks: the roofline denominator (~60 ms microbenchmark, warm GPU)
+    peak = C.c_double(0.0)
+    if lib.picard_fp64_peak_probe(C.c_int32(local_rank), C.c_double(60.0), C.byref(peak)) != 0 or not (peak.value > 1.0):
+        peak_tflops, peak_source = FP64_PEAK_FALLBACK_TFLOPS, "round-1 DMMA microbenchmark (profiles/microbench/fp64_pipes_r01.jsonl): the in-run probe failed"
+    else:
+        peak_tflops = peak.value
+        peak_source = ("FP64 DMMA m8n8k4 microbenchmark run by this process right before the timed region (picard_fp64_peak_probe, "
+                       "148 SMs x 8 warps x 8 chains); MEASURED_PEAKS.json has no FP64 entry")
     s0 = core.stats()
     barrier()
     sampler = ClockSampler(local_rank); sampler.start()
@@ -318,7 +369,7 @@ def _main(out):
     d = {k_: s1[k_] - s0[k_] for k_ in s1}
     value = args.steps / (dev_ms / 1e3)
 
-    # ---- roofline of the dominant kernel: the fused pass (falls back to grad / loss variants if none ran)
+    # ---- roofline of the dominant kernel: the pass kind with the largest share of the timed region
     n2t = float(n) * n * t_local
     cand = [("fused", 4.0 * n2t, d["fused_passes"], d["pass_ms_fused"]), ("grad", 4.0 * n2t, d["grad_passes"], d["pass_ms_grad"]),
             ("loss", 2.0 * n2t, d["loss_passes"], d["pass_ms_loss"]), ("grady", (2.0 if wl["ortho"] else 4.0) * n2t, d["grady_passes"], d["pass_ms_grady"])]
@@ -328,36 +379,76 @@ def _main(out):
         name, flops, cnt, ms = max(cand, key=lambda c: c[3])
         avg_ms = ms / cnt
         ach = flops / (avg_ms * 1e-3) / 1e12
-        # the LOSS pass of a whitened 64 < N <= 128 problem runs on the INT8 tensor cores (i8_loss.cu) unless PICARD_I8=0
-        i8 = name == "loss" and 64 < n <= 128 and os.environ.get("PICARD_I8", "") != "0"
-        kname = {"loss": "loss_i8_kernel (LOSS + Y store on tcgen05.mma kind::i8, 28 slice products)" if i8 else "rb_loss_kernel (LOSS + Y store)",
-                 "grady": "rb_grady_kernel (stored-Y gradient)"}.get(name, f"pass_kernel<{name}>")
-        roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": ach / FP64_PEAK_TFLOPS,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture at c3 on one GPU
-                # (profiles/summary_r01f.txt), scaled to this rank's share of the samples; null for kernels not captured
-                "traffic": {"loss": I8_LOSS_TRAFFIC if i8 else 20.436e9, "grady": 10.248e9}.get(name, None) and
-                {"loss": I8_LOSS_TRAFFIC if i8 else 20.436e9, "grady": 10.248e9}[name] * (t_local / 1e7) * (n / 128.0)
-                if (n == 128) else None,
-                # LOSS: read x1 (8 B / element; its 7-slice INT8 image is 7.06 B / element) and write Y' (8 B); gradient: read Y'
-                "algorithmic_bytes": ((15.0625 if i8 else 16.0) if name == "loss" else 8.0) * n * t_local, "avg_launch_ms": avg_ms, "launches": cnt,
-                "flops_per_launch": flops, "peak_source": "FP64 DMMA m8n8k4 microbenchmark measured by us "
-                "(profiles/microbench/fp64_pipes_r01.jsonl); MEASURED_PEAKS.json has no FP64 entry",
-                "share_of_step": ms / dev_ms, "hbm_gbs": 8.0 * n * t_local / (avg_ms * 1e-3) / 1e9}
+        i8 = (name == "loss" and d["i8_loss_passes"] == d["loss_passes"]) or (name == "grady" and d["i8_grad_passes"] == d["grady_passes"])
+        kname = {"loss": "loss_i8_kernel (LOSS pass of a line-search try + Y' store; tcgen05.mma kind::i8, 21 digit products)" if i8
+                 else "rb_loss_kernel (LOSS + Y store, FP64 DMMA)",
+                 "grady": "grad_i8_kernel (stored-Y gradient; tcgen05.mma kind::i8, 21 digit products)" if i8
+                 else "rb_grady_kernel (stored-Y gradient, FP64 DMMA)"}.get(name, f"pass_kernel<{name}>")
+        traffic, traffic_src = NCU_TRAFFIC_C3.get(name, (None, None)) if (n == 128 and i8) else (None, None)
+        # LOSS: read the digit image of x1 (6.03 B / element) and write Y' (8 B); FP64 LOSS: read x1 (8 B), write Y'; gradient: read Y'
+        # (the INT8 gradient kernel's two column halves each read Y': the second read is an L2 hit)
+        alg_bytes = ((14.03125 if i8 else 16.0) if name == "loss" else 8.0) * n * t_local
+        roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops,
+                "traffic": traffic * (t_local / 1e7) if traffic else None, "traffic_source": traffic_src,
+                "algorithmic_bytes": alg_bytes, "avg_launch_ms": avg_ms, "launches": cnt, "flops_per_launch": flops,
+                "peak_source": peak_source, "share_of_step": ms / dev_ms, "hbm_gbs": alg_bytes / (avg_ms * 1e-3) / 1e9,
+                "what": "achieved = ALGORITHMIC f64 flops of the pass (2 N^2 T_local) / mean launch duration; peak = FP64 tensor peak "
+                        "(BASELINE.md's roofline).  The INT8 engines reach the f64 result through exact digit splitting, so frac can "
+                        "exceed 1: the `engine` object gives the integer-op view"}
         if i8:
-            # achieved / peak above stay on the ALGORITHMIC f64 flops of the pass (2 N^2 T) against the FP64 tensor peak -- the
-            # roofline BASELINE.md defines; what the tensor cores actually execute is 28 INT8 products of that shape:
-            ops = 28.0 * 2.0 * 128 * 128 * t_local
-            roof["engine"] = {"what": "error-free 7-slice INT8 splitting, s32 accumulators in TMEM, result within 2e-13 of f64 (tools/ozaki_numerics.py)",
-                              "int8_tops": ops / (avg_ms * 1e-3) / 1e12, "int8_peak_nominal_tops": 4500.0,
-                              "int8_ceiling_for_128x32x32_mma_tops": 1484.8,
-                              "ceiling_source": "profiles/microbench/umma_i8_probe_r01.jsonl: 51 cycles per MMA whatever N <= 64; TMEM (512 columns) "
-                                                "holds 7 level accumulators + the W' slices only for N = 32"}
+            ops = 21.0 * 2.0 * 128 * 128 * t_local
+            roof["engine"] = {"what": "error-free balanced radix-256 splitting, 6 digits, 21 digit products, s32 accumulators in TMEM "
+                                      "(tests/host/i8_split_check.cpp: within 3e-13 of f64)",
+                              "int8_tops": ops / (avg_ms * 1e-3) / 1e12, "int8_peak_nominal_tops": 4500.0}
+        roof["all_passes"] = {nm: {"launches": c, "avg_ms": m / c, "tflops_f64_equivalent": f / (m / c * 1e-3) / 1e12}
+                              for nm, f, c, m in cand}
     pass_mix = {"fused": d["fused_passes"], "grad": d["grad_passes"], "loss": d["loss_passes"], "ls_tries": d["ls_tries"],
                 "fallbacks": d["fallbacks"], "sign_changes": d["sign_changes"], "restarts": restarts, "grady": d["grady_passes"],
+                "i8_loss": d["i8_loss_passes"], "i8_grad": d["i8_grad_passes"],
                 "pass_ms": {"fused": d["pass_ms_fused"], "grad": d["pass_ms_grad"], "loss": d["pass_ms_loss"], "grady": d["pass_ms_grady"]}}
+    pass_ms_total = d["pass_ms_fused"] + d["pass_ms_grad"] + d["pass_ms_loss"] + d["pass_ms_grady"]
+    non_pass_ms_per_step = (dev_ms - pass_ms_total) / args.steps  # this rank's own split (pass times are per rank)
     state = core.state()
     core.close()
+
+    # ---- parity beside the measurement: on the data that was just timed
+    parity = None
+    if not args.no_parity:
+        import _data
+        from oracle import oracle as orc
+        wp = np.ascontiguousarray(_data.orthogonal(n, 7) + 0.01 * np.random.default_rng(11).standard_normal((n, n)))
+        kind_c, alpha_c, want_h = wl["kind"], wl["alpha"], not wl["ortho"]
+
+        def moments_dev(flags):
+            gr = np.zeros((n, n)); sd = np.zeros(n); hr = np.zeros((n, n)); sq = np.zeros(n); lrow = np.zeros(n)
+            stt = _ffi.Stats(); e2 = C.create_string_buffer(1024)
+            rc = lib.picard_eval_moments_device_ex(C.c_void_p(x1_dev.data_ptr()), C.c_int64(n), C.c_int64(t_local), C.c_int64(ld), hp(wp),
+                                                   C.c_int32(kind_c), C.c_double(alpha_c), C.c_int32(3), C.c_int32(int(want_h)),
+                                                   C.c_int32(local_rank), C.c_uint32(flags), C.c_int32(int(wl["extended"])), C.c_int32(0),
+                                                   None, hp(gr), hp(sd), hp(hr), hp(sq), hp(lrow), C.byref(stt), e2, C.c_size_t(1024))
+            assert rc == 0, e2.value
+            return dict(gr=gr, sd=sd, hr=hr, sq=sq, lrow=lrow), stt.as_dict()
+
+        parity = {"tolerance": 1e-10, "definition": "max|a - b| / max|b| per quantity (BASELINE.json north_star)", "w": "orthogonal(seed 7) + 0.01 N(0,1)"}
+        keys = ("gr", "sd", "lrow") + (("hr", "sq") if want_h else ())
+        default, st_def = moments_dev(0)
+        fp64, st_fp = moments_dev(P.FLAG_NO_INT8)
+        parity["default_engine_vs_fp64_kernels_full_T"] = {
+            "t_local": int(t_local), "engine": {"i8_loss_passes": st_def["i8_loss_passes"], "i8_grad_passes": st_def["i8_grad_passes"],
+                                                "i8_fallbacks": st_def["i8_fallbacks"], "i8_range": st_def["i8_range"]},
+            **{k_: _data.rel_err(default[k_], fp64[k_]) for k_ in keys}}
+        if rank == 0:
+            ts = int(min(t_local, 100_000))
+            xs = x1_dev[:, :ts].cpu().numpy()
+            ref = orc.eval_point(xs, wp, kind_c, alpha_c, ortho=False, extended=False)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import _gpu
+            got, st_s = _gpu.eval_moments_ex(xs, wp, kind_c, alpha_c, mode=3, want_h=want_h, whitened=bool(wl["extended"]), device=local_rank)
+            parity["default_engine_vs_oracle_slice"] = {"t": ts, "i8_loss_passes": st_s["i8_loss_passes"], "i8_grad_passes": st_s["i8_grad_passes"],
+                                                        **{k_: _data.rel_err(got[k_], getattr(ref, k_)) for k_ in keys}}
+        worst = max([v for blk in parity.values() if isinstance(blk, dict) for k_, v in blk.items() if k_ in keys] or [0.0])
+        parity["worst"] = worst
+        parity["ok"] = bool(worst <= 1e-10)
     del x1_dev
 
     # ---- e2e: the reference-facing call on host buffers (rank-local shard), H2D + whole fit + D2H timed
@@ -398,21 +489,20 @@ def _main(out):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_oracle_rate(wl, args.cpu_t, args.cpu_iters, os.cpu_count() or 1)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"oracle core loop N={n}, T={r['t_cpu']}, {r['iters']} outer iterations in {r['seconds']:.2f} s "
-                         f"({r['it_s_sample']:.3f} it/s), scaled linearly in T to T={t_total}"}
+        r = cpu_oracle_rate(wl, args.cpu_t, 1, args.cpu_iters, os.cpu_count() or 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "host": host_description(),
+               "sample": f"oracle core loop (C++ port of core.rs on OpenBLAS) N={n}, T={r['t_cpu']}: 1 warm-up + {r['iters']} timed outer "
+                         f"iterations in {r['seconds']:.2f} s ({r['it_s_sample']:.4f} it/s on the sample), scaled linearly in T to T={t_total}"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload, "n": n, "t_total": t_total, "t_per_gpu": t_local,
-                       "parallelism": f"sample-sharded x{world}", "l2": "inputs (8*N*T_local bytes per pass) far exceed the 126 MB L2",
-                       "timing": "CUDA events on the library stream around picard_core_run; wall clock cross-check in wall_ms_per_step"},
+            "config": config_dict(args, wl, world, t_total, shard_range(t_total, 0, world)[1] - shard_range(t_total, 0, world)[0]),
             "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks, "e2e": e2e, "gpu_launches": int(d["kernel_launches"]),
-            "roofline": roof, "cpu_baseline": cpu, "passes": pass_mix,
+            "roofline": roof, "cpu_baseline": cpu, "passes": pass_mix, "parity": parity,
+            "non_pass_ms_per_step": non_pass_ms_per_step,
             "state": {"n_iterations": state["n_iterations"], "gradient_norm": state["gradient_norm"], "loss": state["loss"]},
         }
         print(json.dumps(line), file=out, flush=True)

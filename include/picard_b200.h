@@ -230,6 +230,10 @@ int picard_synth_sources(double* d_out, int64_t n, int64_t n_samples, int64_t ld
 int picard_apply_device(const double* a, const double* mean, int64_t n_out, int64_t n_in, const double* d_in, int64_t ld_in,
                         double* d_out, int64_t ld_out, int64_t n_samples, int32_t device, void* stream);
 
+/* Measurement hook: FP64 tensor-core (DMMA m8n8k4) peak of the device at its current clocks, in TFLOP/s, from a microbenchmark
+ * of about budget_ms milliseconds.  bench.py's roofline denominator (the pool's MEASURED_PEAKS.json has no FP64 figure). */
+int picard_fp64_peak_probe(int32_t device, double budget_ms, double* tflops);
+
 /* ---- multi-GPU plumbing: one process per GPU, NCCL over NVLink ------------------------------------ */
 #define PICARD_UNIQUE_ID_BYTES 128
 int picard_comm_unique_id(char id[PICARD_UNIQUE_ID_BYTES]); /* call on one rank, broadcast out of band */

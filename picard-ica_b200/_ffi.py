@@ -17,7 +17,7 @@ EXPORTED = [
     "picard_core_reset", "picard_core_state", "picard_core_stats", "picard_core_destroy", "picard_eval_moments", "picard_eval_moments_ex",
     "picard_eval_moments_device", "picard_eval_moments_device_ex",
     "picard_eval_point", "picard_matrix_exp", "picard_sln_det", "picard_sym_decorrelation", "picard_compute_direction",
-    "picard_center_whiten", "picard_center_whiten_device", "picard_jade", "picard_jade_cumulants", "picard_synth_sources", "picard_apply_device", "picard_comm_unique_id",
+    "picard_center_whiten", "picard_center_whiten_device", "picard_jade", "picard_jade_cumulants", "picard_synth_sources", "picard_fp64_peak_probe", "picard_apply_device", "picard_comm_unique_id",
     "picard_comm_create", "picard_comm_rank", "picard_comm_size", "picard_comm_destroy",
 ]
 

@@ -440,6 +440,14 @@ int picard_synth_sources(double* d_out, int64_t n, int64_t n_samples, int64_t ld
   });
 }
 
+int picard_fp64_peak_probe(int32_t device, double budget_ms, double* tflops) {
+  return guarded(nullptr, 0, [&] {
+    DeviceGuard guard(device);
+    const double v = aux::fp64_peak_probe(guard.sm_count, budget_ms, 0);
+    if (tflops) *tflops = v;
+  });
+}
+
 int picard_apply_device(const double* a, const double* mean, int64_t n_out, int64_t n_in, const double* d_in, int64_t ld_in,
                         double* d_out, int64_t ld_out, int64_t n_samples, int32_t device, void* stream) {
   return guarded(nullptr, 0, [&] {

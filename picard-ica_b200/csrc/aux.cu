@@ -1,5 +1,7 @@
 // Auxiliary HBM-bound kernels: row sums for centering (whitening.rs:24-35) and the counter-based synthetic
 // source generator of the benchmark.
+#include <cmath>
+
 #include "engine.cuh"
 
 namespace picard {
@@ -95,5 +97,47 @@ int synth_sources(double* d_out, int n, int64_t t_local, int64_t ld, int64_t t_o
   return 1;
 }
 
+
+// FP64 tensor peak of THIS device at its CURRENT clocks: every warp runs eight independent DMMA.8x8x4 accumulator chains
+// (the pipe saturates with two chains per scheduler; profiles/microbench/dmma_latency_r01.jsonl).  bench.py runs it right
+// before the timed region and uses the result as the roofline denominator (MEASURED_PEAKS.json has no FP64 entry).
+namespace {
+__global__ void __launch_bounds__(256) dmma_probe_kernel(int iters, double* __restrict__ sink) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ptx::dmma(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) sink[0] = s;  // never true: keeps the chains alive
+}
+}  // namespace
+
+double fp64_peak_probe(int sm_count, double budget_ms, cudaStream_t st) {
+  DevBuf<double> sink(1);
+  cudaEvent_t e0, e1;
+  PICARD_CUDA(cudaEventCreate(&e0)); PICARD_CUDA(cudaEventCreate(&e1));
+  const int grid = sm_count * 4;
+  int iters = 20000;
+  double best = 0.0, spent = 0.0;
+  for (int rep = 0; rep < 12 && spent < budget_ms; ++rep) {
+    PICARD_CUDA(cudaEventRecord(e0, st));
+    dmma_probe_kernel<<<grid, 256, 0, st>>>(iters, sink.p);
+    PICARD_CUDA(cudaEventRecord(e1, st));
+    PICARD_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PICARD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    spent += ms;
+    const double flops = (double)grid * 8.0 /* warps */ * 8.0 /* chains */ * (double)iters * 512.0;  // m8n8k4: 256 FMA per warp instruction
+    if (rep > 0) best = std::fmax(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return best;
+}
 }  // namespace aux
 }  // namespace picard

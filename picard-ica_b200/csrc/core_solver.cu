@@ -236,6 +236,10 @@ void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
   const bool use_i8 = mode == PASS_LOSS && dens != DENS_LINEAR && i8_prepare();
   const bool use_i8_grad = mode == PASS_GRADY && i8_state_ == 1 && i8_grad_supported(dims_.n, dens, want_h);
   if (use_i8_grad) stats_.kernel_launches += i8_row_exponents(d_w, dims_.n, xstats_.p, rowexp_.p, st_);
+  if (mode == PASS_FUSED) stats_.fused_passes++;
+  else if (mode == PASS_GRAD) stats_.grad_passes++;
+  else if (mode == PASS_GRADY) stats_.grady_passes++;
+  else stats_.loss_passes++;
   PICARD_CUDA(cudaEventRecord(ev_a_, st_));
   if (use_i8) { stats_.kernel_launches += launch_loss_i8(L, xs8_.p, wblob8_.p); stats_.i8_loss_passes++; }
   else if (use_i8_grad) { stats_.kernel_launches += launch_grad_i8(L, rowexp_.p); stats_.i8_grad_passes++; }
@@ -254,10 +258,6 @@ void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
 }
 
 void CoreSolver::pass(const double* d_w, int mode, double* d_mom) {
-  if (mode == PASS_FUSED) stats_.fused_passes++;
-  else if (mode == PASS_GRAD) stats_.grad_passes++;
-  else if (mode == PASS_GRADY) stats_.grady_passes++;
-  else stats_.loss_passes++;
   eval_pass(d_w, mode, need_h_, dens_, alpha_, d_mom, /*store_y=*/true);  // LOSS mode: want_h = the Sq row sums only
 }
 
@@ -341,7 +341,6 @@ int64_t CoreSolver::run(int64_t max_new) {
     if (dims_.extended && !cov_identity_) {
       // C = Y Y^T / T once, never updated (core.rs:199-205, quirk Q5): a LINEAR gradient pass gives sum y y^T
       eval_pass(W_, PASS_GRAD, false, DENS_LINEAR, 1.0, mom_trial_);
-      stats_.grad_passes++;
       stats_.kernel_launches += small::copy_scaled(mom_trial_ + mom_off_gr(n), C_, (int64_t)n * n, 1.0 / dims_.t_total, st_);
     }
     started_ = true;
@@ -441,12 +440,10 @@ void CoreSolver::fastica(int64_t iters, double* w_host) {
   for (int64_t it = 0; it < iters; ++it) {
     if (from_x) {
       eval_pass(W_, PASS_GRAD, false, dens_, alpha_, mom_cur_);
-      stats_.grad_passes++;
     } else {  // N > 128: Y = W X kept by a LOSS pass, moments from the stored Y
       if (!ybuf_.p) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: no memory for the Y store (needed for N > 128)");
       eval_pass(W_, PASS_LOSS, false, dens_, alpha_, mom_cur_, true);
       eval_pass(W_, PASS_GRADY, false, dens_, alpha_, mom_cur_);
-      stats_.loss_passes++; stats_.grady_passes++;
     }
     stats_.kernel_launches += small::fastica_matrix(mom_cur_, n, dims_.t_total, W_, tmp.p, Wt_, st_);
     decorrelate(Wt_, W_);

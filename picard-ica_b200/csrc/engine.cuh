@@ -84,6 +84,8 @@ namespace aux {
 // row sums of (n x t_local) X -> d_out (n), deterministic two-stage reduction. work >= n * 1024 doubles.
 int row_sums(const double* d_x, int n, int64_t t_local, int64_t ldx, double* d_work, double* d_out, cudaStream_t st);
 int synth_sources(double* d_out, int n, int64_t t_local, int64_t ld, int64_t t_offset, int n_laplace, uint64_t seed, cudaStream_t st);
+// measured FP64 tensor (DMMA) peak of the current device at its current clocks, TFLOP/s; runs for about budget_ms
+double fp64_peak_probe(int sm_count, double budget_ms, cudaStream_t st);
 }  // namespace aux
 
 // ---- the core loop (core.rs:162-401)

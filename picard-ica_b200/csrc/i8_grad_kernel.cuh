@@ -44,21 +44,30 @@ struct GradGeom {
   static constexpr int NTHREADS = 32 * (NCW + 2);
   static constexpr int FLUSH_TILES = 512;          // 16384 samples between flushes
   static constexpr size_t TAB_BYTES = (size_t)dmath::Tab<true>::EXP_N * 8;  // the exp table only (no log-likelihood here)
-  static constexpr size_t SMEM_BYTES = (size_t)YS * Y_STAGE_BYTES + (size_t)SLOTS * SLOT_BYTES + TAB_BYTES + 1024;
+  static constexpr size_t TAIL_BYTES = 2048;  // barriers (14 x 8), the TMEM slot, [2][64] Sd partials
+  static constexpr size_t SMEM_BYTES = (size_t)YS * Y_STAGE_BYTES + (size_t)SLOTS * SLOT_BYTES + TAB_BYTES + TAIL_BYTES;
   static constexpr uint32_t IDESC = make_idesc(NB);
   static_assert(SMEM_BYTES <= 232448, "shared memory");
   static_assert((long long)S * FLUSH_TILES * KT * 128 * 128 < (1ll << 31), "level sums must stay exact in s32");
 };
 
-// shared-memory matrix descriptor: K-major, SWIZZLE_32B, rows of 32 bytes (one K-step), 8-row groups 256 bytes apart
-__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
+// Operand slot layouts (K-major, one 32-byte K-step per row; 8-row groups 256 bytes apart):
+//   LAYOUT 0: SWIZZLE_32B -- rows of 32 bytes, 16-byte chunk c of row r at chunk position c ^ ((r >> 2) & 1)
+//   LAYOUT 1: no swizzle (interleaved core matrices of 8 rows x 16 bytes) -- chunk c of row r at (r >> 3) 256 + c 128 + (r & 7) 16
+// Both are conflict-free for the converters' STS.64; the library uses LAYOUT 0, profiles/lab checks both on the hardware.
+template <int LAYOUT>
+__device__ __forceinline__ uint64_t make_desc_k32(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;            // LBO: unused for swizzled K-major layouts
-  d |= (uint64_t)(256 >> 4) << 32;   // SBO
-  d |= (uint64_t)1 << 46;            // descriptor version of sm_100
-  d |= (uint64_t)6 << 61;            // SWIZZLE_32B
+  d |= (uint64_t)(LAYOUT == 0 ? 1 : (128 >> 4)) << 16;  // LBO: K-adjacent core matrices (unused for swizzled K-major layouts)
+  d |= (uint64_t)(256 >> 4) << 32;                      // SBO: 8-row groups
+  d |= (uint64_t)1 << 46;                               // descriptor version of sm_100
+  d |= (uint64_t)(LAYOUT == 0 ? 6 : 0) << 61;           // SWIZZLE_32B / SWIZZLE_NONE
   return d;
+}
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t slot_row_offset(int row, int chunk) {
+  return LAYOUT == 0 ? (uint32_t)(row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4)) : (uint32_t)((row >> 3) * 256 + chunk * 128 + (row & 7) * 16);
 }
 
 // 8 values v[i] (|v[i] sc| <= 2^46) -> their six balanced digits, packed per digit: w[p][h] holds byte p (p = 0 least significant,
@@ -106,7 +115,7 @@ struct GradParams {
 #define I8_TRACE_SLOTS 0
 #endif
 
-template <int DENS, int ABL = 0>
+template <int DENS, int ABL = 0, int LAYOUT = 0>
 __global__ void __launch_bounds__(GradGeom::NTHREADS, 1)
 grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, long long* __restrict__ trace) {
   using G = GradGeom;
@@ -123,7 +132,8 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
   uint64_t* f_full = o_empty + G::SLOTS;          // accumulators complete up to a flush point (commit)
   uint64_t* f_empty = f_full + 1;                 // accumulators read back (NCW warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(f_empty + 1);
-  double* sdsm = reinterpret_cast<double*>(tmem_slot + 2);  // [4][64]: Sd partials of the four sample groups
+  double* sdsm = reinterpret_cast<double*>(tmem_slot + 2);  // [2][64]: Sd partials of the two sample halves
+  static_assert((2 * G::YS + 2 * G::SLOTS + 2) * 8 + 8 + 2 * 64 * 8 <= G::TAIL_BYTES, "shared-memory tail");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = blockIdx.x & 1, tg = blockIdx.x >> 1, n_tg = gridDim.x >> 1;
@@ -177,7 +187,7 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
 #pragma unroll
           for (int pa = 0; pa <= d; ++pa) {
             const int qb = d - pa;
-            umma_i8_ss(tmem + (uint32_t)(d * G::NB), make_desc_sw32(a0 + pa * G::A_DIGIT_BYTES), make_desc_sw32(b0 + qb * G::B_DIGIT_BYTES),
+            umma_i8_ss(tmem + (uint32_t)(d * G::NB), make_desc_k32<LAYOUT>(a0 + pa * G::A_DIGIT_BYTES), make_desc_k32<LAYOUT>(b0 + qb * G::B_DIGIT_BYTES),
                        G::IDESC, (since_flush > 0 || pa > 0) ? 1u : 0u);
           }
         }
@@ -206,9 +216,9 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
     const double sc_y = scalbn(1.0, FRAC_BITS - ey), sc_psi = scalbn(1.0, FRAC_BITS - p.psi_exp);
     // Y stage: box g >> 1, row r, 16-byte chunks 4 (g & 1) + i at position chunk ^ (r & 7)
     const uint32_t y_off = (uint32_t)((g >> 1) * (G::Y_STAGE_BYTES / 2) + r * 128);
-    // operand slot rows of 32 bytes: 16-byte chunk (g >> 1) ^ ((row >> 2) & 1), byte 8 (g & 1) within it
-    const uint32_t a_off = (uint32_t)(r * 32 + ((((g >> 1) ^ ((r >> 2) & 1))) << 4) + 8 * (g & 1));
-    const uint32_t b_off = (uint32_t)(S * G::A_DIGIT_BYTES + rl * 32 + ((((g >> 1) ^ ((rl >> 2) & 1))) << 4) + 8 * (g & 1));
+    // operand slot: this thread's 8 bytes of a row = half (g & 1) of the 16-byte chunk g >> 1
+    const uint32_t a_off = slot_row_offset<LAYOUT>(r, g >> 1) + 8 * (g & 1);
+    const uint32_t b_off = (uint32_t)(S * G::A_DIGIT_BYTES) + slot_row_offset<LAYOUT>(rl, g >> 1) + 8 * (g & 1);
     double sd = 0.0;
     // flush ownership: TMEM lane quarter warp & 3, 16 accumulator columns (warp >> 2) * 16 ..
     const int q4 = warp & 3, cg = warp >> 2;

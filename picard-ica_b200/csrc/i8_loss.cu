@@ -29,7 +29,7 @@ template <int DENS, bool WANT_SQ>
 static int launch_loss_i8_one(const PassLaunch& L, const uint8_t* xblob, uint8_t* wblob) {
   using G = i8::LossGeom<I8_TILE>;
   auto kern = i8::loss_i8_kernel<DENS, WANT_SQ, I8_TILE, 0>;
-  const CUtensorMap tmap_out = L.d_out != nullptr ? make_tmap(L.d_out, L.ld_out, L.t_local, L.n_out, 128) : CUtensorMap{};
+  const CUtensorMap tmap_out = L.d_out != nullptr ? make_tmap_box(L.d_out, L.ld_out, L.t_local, L.n_out, G::CPT, 32, false) : CUtensorMap{};
   static PerDeviceInt configured;  // per instantiation and per device
   configured.get([&] {
     PICARD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));

@@ -15,9 +15,13 @@
 //                        the MMAs only read the B operand from shared memory; tcgen05.commit releases the ring stage and
 //                        publishes the accumulators
 //   warps 0-15         : epilogue, thread = (row = TMEM lane, NT / 4 samples): tcgen05.ld of the 6 levels, accumulators returned
-//                        at once, exact 64-bit combination, scaling by exponent adds, log-likelihood (density.cuh), row sums per
-//                        thread; Y' through shared memory and TMA stores of [128 rows x 16 samples] boxes (the unit clips the
-//                        ragged last tile and the rows >= n_out); warps 0-3 first store W' into tensor memory
+//                        at once, exact 64-bit combination, scaling by exponent adds, log-likelihood, row sums per thread; Y'
+//                        through shared memory and ONE TMA store per warp and tile of its own [32 rows x NT / 4 samples] box
+//                        (no CTA-wide barrier: the warps only meet at the accumulator hand-over; the unit clips the ragged last
+//                        tile and the rows >= n_out); warps 0-3 first store W' into tensor memory
+// tanh log-likelihood without a logarithm per element: sum_t [|y| + log(1 + e_t) / a] = sum |y| + log(prod (1 + e_t)) / a with
+// e_t = exp(-2 a |y_t|): the factors lie in [1, 2], so a thread keeps a running product, moves its exponent into an integer counter
+// once per tile and takes ONE logarithm at the end of the kernel (relative error of the product ~ sqrt(#factors) 2^-53).
 // ABL (ablation bits, profiles/lab only; the library instantiates ABL = 0): 1 = no density, 2 = no Y' store, 4 = trace.
 // =====================================================================================================
 #pragma once
@@ -46,11 +50,12 @@ struct LossGeom {
   static constexpr int CPT = NT / 4;                               // samples per epilogue thread and tile
   static_assert(CPT % 4 == 0, "tcgen05.ld x4 / x8 granularity");
   static constexpr int NTHREADS = 32 * (NEW + 2);
-  static constexpr int NBOX = NT / 16;                             // TMA store boxes per tile
-  static constexpr size_t SMEM_Y = (size_t)2 * 128 * NT * 8;       // Y' tile, two buffers of NBOX [128 rows][16 samples] SWIZZLE_128B boxes
+  static constexpr int YBOX_DOUBLES = 32 * CPT;                    // a warp's Y' box: [32 rows][CPT samples], dense
+  static constexpr size_t SMEM_Y = (size_t)2 * NEW * YBOX_DOUBLES * 8;  // two boxes per epilogue warp
   static constexpr size_t SMEM_B = (size_t)NSTAGE * STAGE_BYTES;
-  static constexpr bool BIG = true;                                // density tables (80 KB)
-  static constexpr size_t SMEM_BYTES = SMEM_Y + SMEM_B + (size_t)dmath::Tab<BIG>::DOUBLES * 8 + 8192 /* sums */ + 256;
+  static constexpr bool BIG = true;                                // the 2048-entry exp table (16 KB); the log table is not needed
+  static constexpr size_t TAB_BYTES = (size_t)dmath::Tab<BIG>::EXP_N * 8;
+  static constexpr size_t SMEM_BYTES = SMEM_Y + SMEM_B + TAB_BYTES + 8192 /* sums */ + 256;
   static constexpr uint32_t IDESC = make_idesc(NT);
 };
 
@@ -177,7 +182,7 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
   double* ysm = reinterpret_cast<double*>(smem);
   unsigned char* sb = smem + G::SMEM_Y;
   double* tab = reinterpret_cast<double*>(smem + G::SMEM_Y + G::SMEM_B);
-  double* sums = tab + dmath::Tab<BIG>::DOUBLES;  // [NEW / 4 - 1][2][128]: partial row sums of the column quarters
+  double* sums = tab + dmath::Tab<BIG>::EXP_N;  // [NEW / 4 - 1][2][128]: partial row sums of the column quarters
   uint64_t* bars = reinterpret_cast<uint64_t*>(sums + 1024);
   uint64_t* a_full = bars;                 // W' digits stored in tensor memory (4 warps)
   uint64_t* b_full = bars + 1;             // [NSTAGE] tile landed (transaction bytes)
@@ -188,7 +193,7 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr bool NEED_TAB = !NO_DENS && (DENS == DENS_TANH || DENS == DENS_EXP);
-  if (NEED_TAB) load_density_tables<BIG>(tab, DENS == DENS_TANH, tid, G::NTHREADS);
+  if (NEED_TAB) load_density_tables<BIG>(tab, false, tid, G::NTHREADS);
   if (tid == 0) {
     ptx::mbar_init(a_full, 4);
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1 + NEW); }
@@ -249,7 +254,8 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
     // =================================== epilogue ===================================
     const int q4 = warp & 3, cq = warp >> 2;   // TMEM lane quarter of this warp, column quarter of the tile
     const int row = 32 * q4 + lane;
-    double sl = 0.0, sq = 0.0;
+    double sl = 0.0, sq = 0.0, prod = 1.0;
+    int pexp = 0;
     if (cq == 0) {  // warps 0-3: this thread's row of every W' digit into tensor memory (4 K-steps of 32 bytes = 8 columns each)
 #pragma unroll 1
       for (int pa = 0; pa < S; ++pa) {
@@ -305,51 +311,50 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
       // log-likelihood / y^2 row sums
       if (!NO_DENS) {
         const bool partial_tile = (t0 + CPT > p.t_local);
-        if (!partial_tile) {
 #pragma unroll
-          for (int e = 0; e < CPT; ++e) {
-            double f = 0.0, fd = 0.0, dsd = 0.0;
-            density_eval<DENS, false, true, BIG>(y[e], p.dp, tab, f, fd, dsd, sl);
-            if (WANT_SQ) sq = fma(y[e], y[e], sq);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < CPT; ++e) {
+        for (int e = 0; e < CPT; ++e) {
+          const bool valid = !partial_tile || (t0 + e < p.t_local);  // loglik(0) != 0: padding columns must not reach L
+          if (DENS == DENS_TANH) {
+            const double ay = fabs(y[e]);
+            const double ez = dmath::exp_scaled<BIG>(dmath::clamp_hi(ay, p.dp.hi_limit), p.dp, tab);  // exp(-2 alpha |y|)
+            sl += ay;  // |0| = 0: no mask needed
+            prod *= (partial_tile && !valid) ? 1.0 : 1.0 + ez;
+          } else {
             double f = 0.0, fd = 0.0, dsd = 0.0, dl = 0.0;
             density_eval<DENS, false, true, BIG>(y[e], p.dp, tab, f, fd, dsd, dl);
-            if (t0 + e < p.t_local) {
-              sl += dl;
-              if (WANT_SQ) sq = fma(y[e], y[e], sq);
-            }
+            if (valid) sl += dl;
           }
+          if (WANT_SQ) sq = fma(y[e], y[e], sq);
+        }
+        if (DENS == DENS_TANH) {  // prod in [1, 2^(CPT+1)): its exponent goes to the counter, the mantissa stays in [1, 2)
+          const int h = __double2hiint(prod), k = (h >> 20) - 1023;
+          pexp += k;
+          prod = __hiloint2double(h - (k << 20), __double2loint(prod));
         }
       } else {
 #pragma unroll
         for (int e = 0; e < CPT; ++e) sl += y[e];
       }
       // Y' leaves through shared memory and the TMA unit (a thread's samples are CPT * 8 bytes of ITS row: direct stores would be
-      // 32 different lines per instruction).  Box = 16 samples x 128 rows, SWIZZLE_128B; the unit clips the ragged last tile
-      // and the rows >= n_out.  The buffer of tile it - 2 is free: thread 0 waited for its store group before the last barrier.
+      // 32 different lines per instruction).  One box per warp: [32 rows x CPT samples], dense rows; two buffers, the store of
+      // tile it - 2 has been read by the unit before the buffer is written again (wait_group.read 1 by the issuing lane).
       if (!NO_STORE && p.out != nullptr) {
-        double* yb = ysm + (size_t)(it & 1) * 128 * NT + row * 16;
+        double* yb = ysm + (size_t)(2 * warp + (int)(it & 1)) * G::YBOX_DOUBLES;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
 #pragma unroll
-        for (int e = 0; e < CPT; e += 2) {
-          const int col = CPT * cq + e;  // sample within the tile: box col >> 4, 16-byte chunk (col & 15) >> 1 of the box row
-          *reinterpret_cast<double2*>(yb + (size_t)(col >> 4) * 128 * 16 + ((((col & 15) >> 1) ^ (row & 7)) << 1)) = make_double2(y[e], y[e + 1]);
-        }
+        for (int e = 0; e < CPT; e += 2) *reinterpret_cast<double2*>(yb + lane * CPT + e) = make_double2(y[e], y[e + 1]);
         ptx::fence_proxy_async();
-        if (tid == 0) bulk_wait_read0();
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");
-        if (tid == 0) {
-          const int64_t tt = (tile0 + it * tstride) * NT;
-#pragma unroll
-          for (int b = 0; b < G::NBOX; ++b) tma_store_2d(&tmap_out, ysm + (size_t)(it & 1) * 128 * NT + (size_t)b * 128 * 16, (int)(tt + 16 * b), 0);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_out, yb, (int)((tile0 + it * tstride) * NT + CPT * cq), 32 * q4);
           bulk_commit();
         }
       }
       if (tr) trace[it * 8 + 7] = clock64();
     }
-    if (!NO_STORE && p.out != nullptr && tid == 0) bulk_wait0();
+    if (!NO_STORE && p.out != nullptr && lane == 0) bulk_wait0();
+    if (DENS == DENS_TANH && !NO_DENS) sl = fma(fma((double)pexp, 6.931471805599453094e-01, log(prod)), p.dp.inv_alpha, sl);
     // the column quarters of a row live in warps q4, q4 + 4, q4 + 8, q4 + 12
     if (cq > 0) { sums[(cq - 1) * 256 + row] = sl; sums[(cq - 1) * 256 + 128 + row] = sq; }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");

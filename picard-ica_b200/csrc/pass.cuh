@@ -390,6 +390,7 @@ struct PassLaunch {
 int launch_pass(const PassLaunch& L);
 // TMA tensor map over a (n_rows x t_local) f64 matrix, box = np rows x 16 samples, SWIZZLE_128B, OOB zero fill
 CUtensorMap make_tmap(const double* d_x, int64_t ldx, int64_t t_local, int n_rows, int np);
+CUtensorMap make_tmap_box(const double* d_x, int64_t ldx, int64_t t_local, int n_rows, int box_cols, int box_rows, bool swizzle128);
 int pass_padded_size(int n);  // NP for n (throws if unsupported)
 size_t pass_workspace_doubles(int n, int sm_count);  // partial workspace needed for any mode
 

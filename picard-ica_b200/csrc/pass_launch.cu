@@ -37,25 +37,31 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// X is (n_in x t_local) f64, row-major, leading dimension ldx. Box = 16 samples x NP rows, SWIZZLE_128B;
-// rows >= n_in and samples >= t_local are zero-filled by the TMA unit.
-CUtensorMap make_tmap(const double* d_x, int64_t ldx, int64_t t_local, int n_in, int np) {
+// A (n_rows x t_local) f64 matrix, row-major, leading dimension ldx.  Box = box_cols samples x box_rows rows; SWIZZLE_128B
+// (box_cols = 16: a 128-byte swizzle row) or dense rows.  Rows >= n_rows and samples >= t_local are zero-filled on loads and
+// clipped on stores by the TMA unit.
+CUtensorMap make_tmap_box(const double* d_x, int64_t ldx, int64_t t_local, int n_rows, int box_cols, int box_rows, bool swizzle128) {
   if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0 || (ldx & 1) != 0)
     throw Error(PICARD_INVALID_DIMENSIONS,
                 "Invalid dimensions: device sample matrix must be 16-byte aligned with an even row stride (TMA)");
   if (t_local <= 0 || t_local >= (int64_t)1 << 31)
     throw Error(PICARD_INVALID_DIMENSIONS, "Invalid dimensions: per-GPU sample count must be in [1, 2^31)");
   CUtensorMap m;
-  cuuint64_t gdim[2] = {(cuuint64_t)t_local, (cuuint64_t)n_in};
+  cuuint64_t gdim[2] = {(cuuint64_t)t_local, (cuuint64_t)n_rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ldx * 8};
-  cuuint32_t box[2] = {16, (cuuint32_t)np};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(d_x), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     throw Error(PICARD_COMPUTATION_ERROR, "Computation error: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return m;
+}
+
+// Box = 16 samples x NP rows, SWIZZLE_128B: what the pass kernels load
+CUtensorMap make_tmap(const double* d_x, int64_t ldx, int64_t t_local, int n_in, int np) {
+  return make_tmap_box(d_x, ldx, t_local, n_in, 16, np, true);
 }
 
 int launch_pass(const PassLaunch& L) {

@@ -157,7 +157,6 @@ def test_default_mode_fit_matches_oracle(n, t):
     assert res.converged == ref.converged
     assert amari_distance(res.full_unmixing(), np.linalg.pinv(ref.full_unmixing())) <= 1e-6
     np.testing.assert_array_equal(res.signs, ref.signs)
-    assert amari_distance(res.full_unmixing(), a) < 0.05
 
 
 @pytest.mark.parametrize("n", [96, 128])

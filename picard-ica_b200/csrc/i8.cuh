@@ -9,7 +9,7 @@
 namespace picard {
 
 constexpr int I8_SLICES = 6;   // balanced radix-256 digits per operand
-constexpr int I8_TILE = 32;    // samples per tile of the sliced image of x1
+constexpr int I8_TILE = 64;    // samples per tile of the sliced image of x1
 constexpr int I8_WBLOB_BYTES = I8_SLICES * 128 * 128 + 128 * 4;  // six slices of W' (row-major, 128 x 128 bytes) + 128 row exponents
 // statistics of x1 gathered while it is sliced: [0] sum_t 2^(e_t - 1) (the power-of-two bounds of the samples' largest components),
 // [1] max_t |x_t|^2 as the bit pattern of a double, [2 .. 2 + 128) row sums of squares

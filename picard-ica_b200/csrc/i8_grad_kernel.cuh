@@ -17,11 +17,14 @@
 // One CTA per SM, 18 warps:
 //   warp 16 (one lane) : TMA loads of the Y tiles ([128 rows x 32 samples] f64 as two SWIZZLE_128B boxes) into a YS-stage ring
 //   warp 17 (one lane) : per tile 21 tcgen05.mma (128 x 64 x 32, kind::i8, both operands from shared memory), commit -> slot free
-//   warps 0-15         : converters, thread = (row, 8 samples): y -> fixed point by one FMA (magic-number rounding), digits by one
-//                        64-bit add + byte permutes, STS.64 into the operand slot (K-major rows of 32 bytes, SWIZZLE_32B: one UMMA
-//                        K-step per row); the threads of the CTA's own rows also evaluate psi / psi' and convert psi.  Every
-//                        FLUSH_TILES tiles they read the level accumulators back (tcgen05.ld), combine them exactly and add them
-//                        to the CTA's f64 partial of Gr.
+//   warps 0-15         : converters.  Every thread converts 8 samples of one row of Y (y -> fixed point by one FMA with magic-number
+//                        rounding, digits by one 64-bit add + byte permutes, STS.64 into the operand slot: K-major rows of 32
+//                        bytes, SWIZZLE_32B, one UMMA K-step per row) AND evaluates psi for 4 samples of one of the CTA's own 64
+//                        rows (the same work for every thread: the four warps of a scheduler stay balanced), converts it and
+//                        stores it (STS.32).  Every FLUSH_TILES tiles the warps read the level accumulators back (tcgen05.ld),
+//                        combine them exactly and add them to the CTA's f64 partial of Gr.
+// FP64-pipe economy (the INT8 MMAs and FP64 instructions share a pipe: profiles/microbench/pipe_probe_r02.jsonl): |y|, clamps and
+// sign transfers on the ALU; tanh: Sd = alpha (T - sum tanh^2), one FMA per element instead of psi' and its sum.
 // =====================================================================================================
 #pragma once
 #include "i8.cuh"
@@ -44,7 +47,7 @@ struct GradGeom {
   static constexpr int NTHREADS = 32 * (NCW + 2);
   static constexpr int FLUSH_TILES = 512;          // 16384 samples between flushes
   static constexpr size_t TAB_BYTES = (size_t)dmath::Tab<true>::EXP_N * 8;  // the exp table only (no log-likelihood here)
-  static constexpr size_t TAIL_BYTES = 2048;  // barriers (14 x 8), the TMEM slot, [2][64] Sd partials
+  static constexpr size_t TAIL_BYTES = 3072;  // barriers (14 x 8), the TMEM slot, [4][64] Sd partials
   static constexpr size_t SMEM_BYTES = (size_t)YS * Y_STAGE_BYTES + (size_t)SLOTS * SLOT_BYTES + TAB_BYTES + TAIL_BYTES;
   static constexpr uint32_t IDESC = make_idesc(NB);
   static_assert(SMEM_BYTES <= 232448, "shared memory");
@@ -96,6 +99,36 @@ __device__ __forceinline__ void digits8(const double (&v)[8], double sc, uint32_
   }
 }
 
+// four values -> six words (word p = byte p of the four fixed-point integers)
+__device__ __forceinline__ void digits4(const double (&v)[4], double sc, uint32_t (&w)[S]) {
+  const double MAGIC = 6755399441055744.0;
+  uint32_t lo[4], hi[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double u = fma(v[i], sc, MAGIC);
+    const unsigned long long U = (unsigned long long)__double_as_longlong(u) + DIGIT_BIAS;
+    lo[i] = (uint32_t)U; hi[i] = (uint32_t)(U >> 32);
+  }
+  const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[0], lo[1], 0x7362);
+  const uint32_t u0 = __byte_perm(lo[2], lo[3], 0x5140), u1 = __byte_perm(lo[2], lo[3], 0x7362);
+  const uint32_t v0 = __byte_perm(hi[0], hi[1], 0x5140), v1 = __byte_perm(hi[2], hi[3], 0x5140);
+  w[0] = __byte_perm(t0, u0, 0x5410) ^ 0x80808080u;
+  w[1] = __byte_perm(t0, u0, 0x7632) ^ 0x80808080u;
+  w[2] = __byte_perm(t1, u1, 0x5410) ^ 0x80808080u;
+  w[3] = __byte_perm(t1, u1, 0x7632) ^ 0x80808080u;
+  w[4] = __byte_perm(v0, v1, 0x5410) ^ 0x80808080u;
+  w[5] = __byte_perm(v0, v1, 0x7632) ^ 0x80808080u;
+}
+
+// tanh(alpha y) with |.|, clamp and sign transfer on the ALU: 13 FP64-pipe instructions
+__device__ __forceinline__ double tanh_psi(double y, const DensParams& dp, const double* __restrict__ tab) {
+  const int hy = __double2hiint(y), ha = hy & 0x7fffffff;
+  const double ayc = __hiloint2double(ha < dp.hi_limit ? ha : dp.hi_limit, __double2loint(y));
+  const double e = dmath::exp_scaled<true>(ayc, dp, tab);  // exp(-2 alpha |y|)
+  const double th = dmath::div_seeded(1.0 - e, 1.0 + e);   // tanh(alpha |y|) >= 0
+  return __hiloint2double(__double2hiint(th) | (hy & 0x80000000), __double2loint(th));
+}
+
 // psi exponent: 1.008 |psi| < 2^e for every argument
 inline int psi_exponent(int dens, double alpha) {
   if (dens == DENS_TANH) return 1;                                     // |tanh| <= 1: I <= 2^46
@@ -132,8 +165,8 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
   uint64_t* f_full = o_empty + G::SLOTS;          // accumulators complete up to a flush point (commit)
   uint64_t* f_empty = f_full + 1;                 // accumulators read back (NCW warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(f_empty + 1);
-  double* sdsm = reinterpret_cast<double*>(tmem_slot + 2);  // [2][64]: Sd partials of the two sample halves
-  static_assert((2 * G::YS + 2 * G::SLOTS + 2) * 8 + 8 + 2 * 64 * 8 <= G::TAIL_BYTES, "shared-memory tail");
+  double* sdsm = reinterpret_cast<double*>(tmem_slot + 2);  // [4][64]: Sd partials of the (sample half, sample quarter) warp groups
+  static_assert((2 * G::YS + 2 * G::SLOTS + 2) * 8 + 8 + 4 * 64 * 8 <= G::TAIL_BYTES, "shared-memory tail");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = blockIdx.x & 1, tg = blockIdx.x >> 1, n_tg = gridDim.x >> 1;
@@ -210,16 +243,18 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
     // thread = (row r, sample group g of 8): warp = (row block rb of 16 rows, sample half sh); lane = (row offset, g & 1)
     const int rb = warp & 7, sh = warp >> 3;
     const int r = 16 * rb + (lane >> 1), g = 2 * sh + (lane & 1);
-    const bool own = (r >> 6) == half;          // this thread's row belongs to the CTA's psi half (warp-uniform: 16 rows per warp)
-    const int rl = r & 63;
     const int ey = (r < p.n) ? p.rowexp[r] : 0;
     const double sc_y = scalbn(1.0, FRAC_BITS - ey), sc_psi = scalbn(1.0, FRAC_BITS - p.psi_exp);
     // Y stage: box g >> 1, row r, 16-byte chunks 4 (g & 1) + i at position chunk ^ (r & 7)
     const uint32_t y_off = (uint32_t)((g >> 1) * (G::Y_STAGE_BYTES / 2) + r * 128);
-    // operand slot: this thread's 8 bytes of a row = half (g & 1) of the 16-byte chunk g >> 1
+    // operand slot: this thread's 8 bytes of row r = half (g & 1) of the 16-byte chunk g >> 1
     const uint32_t a_off = slot_row_offset<LAYOUT>(r, g >> 1) + 8 * (g & 1);
-    const uint32_t b_off = (uint32_t)(S * G::A_DIGIT_BYTES) + slot_row_offset<LAYOUT>(rl, g >> 1) + 8 * (g & 1);
-    double sd = 0.0;
+    // psi: 4 samples 8 g + 4 q .. of the own row 64 half + rl, q = r >> 6 (warp-uniform): every thread does the same amount of work
+    const int rl = r & 63, q = r >> 6, rp = 64 * half + rl;
+    const bool from_regs = (q == half);  // the psi row is this thread's own Y row: the values are already in registers
+    const uint32_t yp_off = (uint32_t)((g >> 1) * (G::Y_STAGE_BYTES / 2) + rp * 128);
+    const uint32_t b_off = (uint32_t)(S * G::A_DIGIT_BYTES) + slot_row_offset<LAYOUT>(rl, g >> 1) + 8 * (g & 1) + 4 * q;
+    double sd = 0.0;  // tanh: sum of tanh^2 ; other densities: sum of psi'
     // flush ownership: TMEM lane quarter warp & 3, 16 accumulator columns (warp >> 2) * 16 ..
     const int q4 = warp & 3, cg = warp >> 2;
     const int jrow = 32 * q4 + lane;
@@ -254,12 +289,12 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
 
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int st = (int)(it % G::YS), sl = (int)(it % G::SLOTS);
-      const int64_t t0 = (tile0 + it * tstride) * G::KT + 8 * g;
+      const int64_t t0 = (tile0 + it * tstride) * G::KT + 8 * g + 4 * q;  // first of this thread's 4 psi samples
       const bool tr = TRACE && blockIdx.x == 0 && it < I8_TRACE_SLOTS && warp == 0 && lane == 0;
       if (tr) trace[it * 8 + 4] = clock64();
       ptx::mbar_wait(&y_full[st], (uint32_t)((it / G::YS) & 1));
       if (tr) trace[it * 8 + 5] = clock64();
-      double y[8];
+      double y[8], yp[4];
       {
         const unsigned char* yb = ysm + (size_t)st * G::Y_STAGE_BYTES + y_off;
 #pragma unroll
@@ -267,38 +302,52 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
           const double2 v = *reinterpret_cast<const double2*>(yb + ((((4 * (g & 1) + i) ^ (r & 7))) << 4));
           y[2 * i] = v.x; y[2 * i + 1] = v.y;
         }
+        if (from_regs) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) yp[i] = q ? y[4 + i] : y[i];  // q is warp-uniform: a register select, no divergence
+        } else {
+          const unsigned char* ypb = ysm + (size_t)st * G::Y_STAGE_BYTES + yp_off;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double2 v = *reinterpret_cast<const double2*>(ypb + ((((4 * (g & 1) + 2 * q + i) ^ (rp & 7))) << 4));
+            yp[2 * i] = v.x; yp[2 * i + 1] = v.y;
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&y_empty[st]);  // the values are in registers: the stage may be refilled
-      uint32_t wy[S][2], wp[S][2];
+      uint32_t wy[S][2], wp[S];
       digits8(y, sc_y, wy);
-      if (own) {
-        double psi[8];
-        if (!NO_PSI) {
-          const bool partial_tile = (t0 + 8 > p.t_local);
+      {
+        double psi[4];
+        if (NO_PSI) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            double fd = 0.0, dsd = 0.0, dsl = 0.0;
-            density_eval<DENS, true, false, true>(y[e], p.dp, tab, psi[e], fd, dsd, dsl);
-            if (!partial_tile || t0 + e < p.t_local) sd += dsd;  // psi'(0) != 0: padding columns must not reach Sd
+          for (int e = 0; e < 4; ++e) psi[e] = 0.5 * yp[e];
+        } else if (DENS == DENS_TANH) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            psi[e] = tanh_psi(yp[e], p.dp, tab);
+            sd = fma(psi[e], psi[e], sd);  // padding samples have y = 0, tanh = 0: no mask needed
           }
         } else {
+          const bool partial_tile = (t0 + 4 > p.t_local);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) psi[e] = 0.5 * y[e];
+          for (int e = 0; e < 4; ++e) {
+            double fd = 0.0, dsd = 0.0, dsl = 0.0;
+            density_eval<DENS, true, false, true>(yp[e], p.dp, tab, psi[e], fd, dsd, dsl);
+            if (!partial_tile || t0 + e < p.t_local) sd += dsd;  // psi'(0) != 0: padding columns must not reach Sd
+          }
         }
-        digits8(psi, sc_psi, wp);
+        digits4(psi, sc_psi, wp);
       }
       // the slot is free once the MMAs of tile it - SLOTS have completed
       ptx::mbar_wait(&o_empty[sl], (uint32_t)(((it / G::SLOTS) & 1) ^ 1));
       if (tr) trace[it * 8 + 6] = clock64();
       unsigned char* ob = osm + (size_t)sl * G::SLOT_BYTES;
 #pragma unroll
-      for (int pb = 0; pb < S; ++pb)  // byte pb of the fixed-point integer = digit S - 1 - pb
+      for (int pb = 0; pb < S; ++pb) {  // byte pb of the fixed-point integer = digit S - 1 - pb
         *reinterpret_cast<uint2*>(ob + (size_t)(S - 1 - pb) * G::A_DIGIT_BYTES + a_off) = make_uint2(wy[pb][0], wy[pb][1]);
-      if (own) {
-#pragma unroll
-        for (int pb = 0; pb < S; ++pb)
-          *reinterpret_cast<uint2*>(ob + (size_t)(S - 1 - pb) * G::B_DIGIT_BYTES + b_off) = make_uint2(wp[pb][0], wp[pb][1]);
+        *reinterpret_cast<uint32_t*>(ob + (size_t)(S - 1 - pb) * G::B_DIGIT_BYTES + b_off) = wp[pb];
       }
       ptx::fence_proxy_async();  // generic-proxy stores before the tensor core's async-proxy reads
       __syncwarp();
@@ -307,13 +356,19 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
       ++since_flush;
       if (since_flush == G::FLUSH_TILES || it + 1 == my_tiles) { flush(); since_flush = 0; }
     }
-    // Sd of the own rows: the four sample groups of a row live in lanes (g & 1) of warps sh = 0, 1
+    // Sd of the own rows: a row's 32 samples per tile live in lanes (g & 1) of the warps (sh, q) in {0, 1}^2
     sd += __shfl_xor_sync(0xffffffffu, sd, 1);
-    if (own && (lane & 1) == 0) sdsm[sh * 64 + rl] = sd;
+    if ((lane & 1) == 0) sdsm[(2 * sh + q) * 64 + rl] = sd;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * G::NCW) : "memory");
     if (tid < G::NB) {
+      double v = (sdsm[tid] + sdsm[64 + tid]) + (sdsm[128 + tid] + sdsm[192 + tid]);
+      if (DENS == DENS_TANH && !NO_PSI) {  // sum psi' = alpha (valid samples of this CTA - sum tanh^2)
+        const int64_t last = tile0 + (my_tiles - 1) * tstride;
+        const int64_t valid = my_tiles * G::KT - ((my_tiles > 0 && last == p.n_tiles - 1) ? (p.n_tiles * G::KT - p.t_local) : 0);
+        v = p.dp.alpha * ((double)valid - v);
+      }
       double* rs = part + G::NB * G::MA;
-      rs[tid] = sdsm[tid] + sdsm[64 + tid];
+      rs[tid] = v;
       rs[G::NB + tid] = 0.0;
       rs[2 * G::NB + tid] = 0.0;
     }

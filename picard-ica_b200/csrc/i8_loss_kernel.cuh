@@ -38,24 +38,30 @@ static_assert(W_EXP_OFFSET + 128 * 4 == I8_WBLOB_BYTES, "wblob layout");
 
 template <int NT>
 struct LossGeom {
-  static_assert(NT % 16 == 0 && NT >= 16 && NT <= 64, "tile = a multiple of the 16-sample TMA store box and of the UMMA N step");
+  static_assert(NT % 16 == 0 && NT >= 16 && NT <= 64, "tile = a multiple of the UMMA N step");
   static constexpr int SLICE_B_BYTES = NT * KP;                    // one digit of a tile: NT samples x 128 bytes
   static constexpr int TILE_BYTES = S * SLICE_B_BYTES + NT * 4;    // + the NT sample exponents (int)
   static constexpr int STAGE_BYTES = ((TILE_BYTES + 1023) / 1024) * 1024;
   static constexpr int NSTAGE = 2;
   static constexpr int ACC_COLS = S * NT;                          // TMEM columns of the level accumulators of one tile
-  static constexpr int TMEM_A = ACC_COLS;                          // W' digit p, K-step k at column TMEM_A + 8 (4 p + k)
-  static_assert(ACC_COLS + S * 32 <= 512, "tensor memory: 512 columns");
+  static constexpr int TMEM_A = ACC_COLS;                          // W' digit p (p < ATM), K-step k at column TMEM_A + 8 (4 p + k)
+  // W' digits kept in tensor memory: as many as fit next to the accumulators (the most significant ones: digit p takes part in
+  // S - p products); the others are read from shared memory (SWIZZLE_128B image, 16 KB per digit)
+  static constexpr int ATM = (512 - ACC_COLS) / 32 < S ? (512 - ACC_COLS) / 32 : S;
+  static_assert(ATM >= 1 && ACC_COLS + ATM * 32 <= 512, "tensor memory: 512 columns");
   static constexpr int NEW = 16;                                   // epilogue warps: TMEM lane quarter (warp & 3) x column quarter (warp >> 2)
   static constexpr int CPT = NT / 4;                               // samples per epilogue thread and tile
   static_assert(CPT % 4 == 0, "tcgen05.ld x4 / x8 granularity");
   static constexpr int NTHREADS = 32 * (NEW + 2);
   static constexpr int YBOX_DOUBLES = 32 * CPT;                    // a warp's Y' box: [32 rows][CPT samples], dense
-  static constexpr size_t SMEM_Y = (size_t)2 * NEW * YBOX_DOUBLES * 8;  // two boxes per epilogue warp
+  static constexpr int YBUFS = NT <= 32 ? 2 : 1;                   // boxes per warp (one is enough: the unit has read it long before the next tile)
+  static constexpr size_t SMEM_Y = (size_t)YBUFS * NEW * YBOX_DOUBLES * 8;
   static constexpr size_t SMEM_B = (size_t)NSTAGE * STAGE_BYTES;
+  static constexpr size_t SMEM_A = (size_t)(S - ATM) * SLICE_A_BYTES;
   static constexpr bool BIG = true;                                // the 2048-entry exp table (16 KB); the log table is not needed
   static constexpr size_t TAB_BYTES = (size_t)dmath::Tab<BIG>::EXP_N * 8;
-  static constexpr size_t SMEM_BYTES = SMEM_Y + SMEM_B + TAB_BYTES + 8192 /* sums */ + 256;
+  static constexpr size_t SMEM_BYTES = SMEM_Y + SMEM_B + SMEM_A + TAB_BYTES + 8192 /* sums */ + 256;
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
   static constexpr uint32_t IDESC = make_idesc(NT);
 };
 
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(1024) slice_w_kernel(const double* __restrict_
 // the pass
 // ---------------------------------------------------------------------------------------------------
 template <int DENS, bool WANT_SQ, int NT, int ABL = 0>
-__global__ void __launch_bounds__(LossGeom<NT>::NTHREADS, 1)
+__global__ void __launch_bounds__(LossGeom<NT>::NTHREADS, 1)  // 18 warps are allocated as 20: 96 registers per thread
 loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wblob, const __grid_constant__ CUtensorMap tmap_out,
                const PassParams p, long long* __restrict__ trace) {
   using G = LossGeom<NT>;
@@ -181,7 +187,8 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
   extern __shared__ __align__(1024) unsigned char smem[];
   double* ysm = reinterpret_cast<double*>(smem);
   unsigned char* sb = smem + G::SMEM_Y;
-  double* tab = reinterpret_cast<double*>(smem + G::SMEM_Y + G::SMEM_B);
+  unsigned char* sa = smem + G::SMEM_Y + G::SMEM_B;   // W' digits ATM .. S-1 (SWIZZLE_128B image), 1024-byte aligned
+  double* tab = reinterpret_cast<double*>(smem + G::SMEM_Y + G::SMEM_B + G::SMEM_A);
   double* sums = tab + dmath::Tab<BIG>::EXP_N;  // [NEW / 4 - 1][2][128]: partial row sums of the column quarters
   uint64_t* bars = reinterpret_cast<uint64_t*>(sums + 1024);
   uint64_t* a_full = bars;                 // W' digits stored in tensor memory (4 warps)
@@ -224,6 +231,8 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
     // =================================== MMA issue ===================================
     if (lane == 0) {
       ptx::mbar_wait(a_full, 0);
+      tc_fence_after();
+      const uint64_t da0 = make_desc(smem_u32(sa));
       for (int64_t it = 0; it < my_tiles; ++it) {
         const int st = (int)(it % NSTAGE);
         if (TRACE && blockIdx.x == 0 && it < I8_TRACE_SLOTS) trace[it * 8 + 0] = clock64();
@@ -240,9 +249,11 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
           for (int pa = 0; pa <= d; ++pa) {
             const int qb = d - pa;
 #pragma unroll
-            for (int k = 0; k < KP / 32; ++k)
-              umma_i8_ts(tacc, tmem + (uint32_t)(G::TMEM_A + 8 * (4 * pa + k)), db0 + (uint64_t)((qb * G::SLICE_B_BYTES + k * 32) >> 4), G::IDESC,
-                         (pa > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < KP / 32; ++k) {
+              const uint64_t db = db0 + (uint64_t)((qb * G::SLICE_B_BYTES + k * 32) >> 4);
+              if (pa < G::ATM) umma_i8_ts(tacc, tmem + (uint32_t)(G::TMEM_A + 8 * (4 * pa + k)), db, G::IDESC, (pa > 0 || k > 0) ? 1u : 0u);
+              else umma_i8_ss(tacc, da0 + (uint64_t)(((pa - G::ATM) * SLICE_A_BYTES + k * 32) >> 4), db, G::IDESC, (pa > 0 || k > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(&b_empty[st]);  // the ring stage may be refilled once these MMAs have read it (and the epilogue its exponents)
@@ -260,14 +271,21 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
 #pragma unroll 1
       for (int pa = 0; pa < S; ++pa) {
         const uint4* src = reinterpret_cast<const uint4*>(wblob + (size_t)pa * SLICE_A_BYTES + (size_t)row * KP);
+        if (pa < G::ATM) {
 #pragma unroll
-        for (int k = 0; k < KP / 32; ++k) {
-          const uint4 u0 = src[2 * k], u1 = src[2 * k + 1];
-          const uint32_t v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-          tmem_st8(tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(G::TMEM_A + 8 * (4 * pa + k)), v);
+          for (int k = 0; k < KP / 32; ++k) {
+            const uint4 u0 = src[2 * k], u1 = src[2 * k + 1];
+            const uint32_t v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            tmem_st8(tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(G::TMEM_A + 8 * (4 * pa + k)), v);
+          }
+        } else {  // the least significant digits: shared memory, 16-byte chunk c of row r at position c ^ (r & 7)
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            *reinterpret_cast<uint4*>(sa + (size_t)(pa - G::ATM) * SLICE_A_BYTES + row * KP + ((c8 ^ (row & 7)) << 4)) = src[c8];
         }
       }
       tmem_wait_st();
+      ptx::fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
@@ -278,26 +296,39 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
       const int64_t t0 = (tile0 + it * tstride) * NT + CPT * cq;
       const bool tr = TRACE && blockIdx.x == 0 && it < I8_TRACE_SLOTS && warp == 0 && lane == 0;
       if (tr) trace[it * 8 + 4] = clock64();
-      // the level accumulators of this thread's samples; then the accumulators go back to the MMA warp
-      int32_t c[S][CPT];
+      // the level accumulators of this thread's samples, read in two groups of three levels that are combined into 64-bit integers at
+      // once (CPT x 6 raw levels would not fit the 96 registers of a thread at CPT = 16); then the accumulators go back to the MMA warp
       const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(CPT * cq);
       ptx::mbar_wait(acc_full, (uint32_t)(it & 1));
       tc_fence_after();
       if (tr) trace[it * 8 + 5] = clock64();
-#pragma unroll
-      for (int d = 0; d < S; ++d) {
-#pragma unroll
-        for (int o = 0; o + 8 <= CPT; o += 8) tmem_ld8(taddr + (uint32_t)(d * NT + o), &c[d][o]);
-        if (CPT % 8 == 4) tmem_ld4(taddr + (uint32_t)(d * NT + CPT - 4), &c[d][CPT - 4]);
-      }
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
-      if (tr) trace[it * 8 + 6] = clock64();
       double y[CPT];
 #pragma unroll
-      for (int e = 0; e < CPT; ++e) y[e] = combine_levels(c[0][e], c[1][e], c[2][e], c[3][e], c[4][e], c[5][e]);
+      for (int grp = 0; grp < 2; ++grp) {
+        int32_t c[3][CPT];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const uint32_t ta = taddr + (uint32_t)((3 * grp + d) * NT);
+          if (CPT == 16) tmem_ld16(ta, &c[d][0]);
+          else {
+#pragma unroll
+            for (int o = 0; o + 8 <= CPT; o += 8) tmem_ld8(ta + (uint32_t)o, &c[d][o]);
+            if (CPT % 8 == 4) tmem_ld4(ta + (uint32_t)(CPT - 4), &c[d][CPT - 4]);
+          }
+        }
+        tmem_wait_ld();
+        if (grp == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+        }
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) {  // = combine_levels(): hi + 2^-24 lo, rounded once
+          const long long v = (long long)c[0][e] * 65536 + (long long)c[1][e] * 256 + (long long)c[2][e];
+          if (grp == 0) y[e] = (double)v; else y[e] = fma((double)v, 5.9604644775390625e-08 /* 2^-24 */, y[e]);
+        }
+      }
+      if (tr) trace[it * 8 + 6] = clock64();
       // exponents of this thread's samples (bulk-copied with the tile: wait on its barrier for visibility; complete long ago),
       // then the ring stage goes back to the producer
       ptx::mbar_wait(&b_full[st], (uint32_t)((it / NSTAGE) & 1));
@@ -315,9 +346,12 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
         for (int e = 0; e < CPT; ++e) {
           const bool valid = !partial_tile || (t0 + e < p.t_local);  // loglik(0) != 0: padding columns must not reach L
           if (DENS == DENS_TANH) {
-            const double ay = fabs(y[e]);
-            const double ez = dmath::exp_scaled<BIG>(dmath::clamp_hi(ay, p.dp.hi_limit), p.dp, tab);  // exp(-2 alpha |y|)
-            sl += ay;  // |0| = 0: no mask needed
+            // |y| on the ALU, clamped: every FP64-pipe instruction here competes with the tensor core's INT8 MMAs for the pipe
+            // (profiles/microbench/pipe_probe_r02.jsonl)
+            const int hy = __double2hiint(y[e]) & 0x7fffffff;
+            const double ayc = __hiloint2double(hy < p.dp.hi_limit ? hy : p.dp.hi_limit, __double2loint(y[e]));
+            const double ez = dmath::exp_scaled<BIG>(ayc, p.dp, tab);  // exp(-2 alpha |y|)
+            sl += fabs(y[e]);  // |0| = 0: no mask needed (the absolute value is an operand modifier of the add)
             prod *= (partial_tile && !valid) ? 1.0 : 1.0 + ez;
           } else {
             double f = 0.0, fd = 0.0, dsd = 0.0, dl = 0.0;
@@ -339,8 +373,11 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
       // 32 different lines per instruction).  One box per warp: [32 rows x CPT samples], dense rows; two buffers, the store of
       // tile it - 2 has been read by the unit before the buffer is written again (wait_group.read 1 by the issuing lane).
       if (!NO_STORE && p.out != nullptr) {
-        double* yb = ysm + (size_t)(2 * warp + (int)(it & 1)) * G::YBOX_DOUBLES;
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        double* yb = ysm + (size_t)(G::YBUFS * warp + (G::YBUFS == 2 ? (int)(it & 1) : 0)) * G::YBOX_DOUBLES;
+        if (lane == 0) {
+          if (G::YBUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < CPT; e += 2) *reinterpret_cast<double2*>(yb + lane * CPT + e) = make_double2(y[e], y[e + 1]);

@@ -100,12 +100,12 @@ static void print_trace(const char* what, const std::vector<long long>& tr, cons
 template <int ABL>
 static void run_loss(const uint8_t* xblob, const uint8_t* wblob, double* yout, int64_t ld, int64_t t, int n, double* partial, int sms, int reps,
                      long long* d_trace) {
-  using G = i8::LossGeom<32>;
-  auto kern = i8::loss_i8_kernel<DENS_TANH, false, 32, ABL>;
+  using G = i8::LossGeom<I8_TILE>;
+  auto kern = i8::loss_i8_kernel<DENS_TANH, false, I8_TILE, ABL>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
   const CUtensorMap tm = make_tmap_box(yout, ld, t, n, G::CPT, 32, false);
   PassParams p{};
-  p.n_out = n; p.n_in = n; p.t_local = t; p.n_tiles = (t + 31) / 32; p.dp = make_dens_params(DENS_TANH, 1.0); p.partial = partial; p.out = yout; p.ld_out = ld;
+  p.n_out = n; p.n_in = n; p.t_local = t; p.n_tiles = (t + I8_TILE - 1) / I8_TILE; p.dp = make_dens_params(DENS_TANH, 1.0); p.partial = partial; p.out = yout; p.ld_out = ld;
   const int grid = sms;
   float ms = time_ms([&] { kern<<<grid, G::NTHREADS, G::SMEM_BYTES>>>(xblob, wblob, tm, p, d_trace); }, reps);
   CK(cudaGetLastError());
@@ -179,7 +179,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&w, sizeof(double) * n * n));
   CK(cudaMalloc(&partial, sizeof(double) * sms * 2 * (2 * 128 * 128 + 3 * 128)));
   CK(cudaMalloc(&xstats, sizeof(double) * I8_XSTATS));
-  CK(cudaMalloc(&xblob, (size_t)((T + 31) / 32) * i8::LossGeom<32>::TILE_BYTES + 1024)); CK(cudaMalloc(&wblob, I8_WBLOB_BYTES));
+  CK(cudaMalloc(&xblob, (size_t)((T + I8_TILE - 1) / I8_TILE) * i8::LossGeom<I8_TILE>::TILE_BYTES + 1024)); CK(cudaMalloc(&wblob, I8_WBLOB_BYTES));
   CK(cudaMalloc(&rowexp, 128 * sizeof(int)));
   CK(cudaMalloc(&d_trace, I8_TRACE_SLOTS * 8 * sizeof(long long))); CK(cudaMemset(d_trace, 0, I8_TRACE_SLOTS * 8 * sizeof(long long)));
   fill_kernel<<<sms * 8, 256>>>(x, n, T, ld, 1234, 1.0);
@@ -187,11 +187,11 @@ int main(int argc, char** argv) {
   CK(cudaDeviceSynchronize());
 
   // ---- slicing
-  const int64_t n_tiles = (T + 31) / 32;
+  const int64_t n_tiles = (T + I8_TILE - 1) / I8_TILE;
   CK(cudaMemset(xstats, 0, sizeof(double) * I8_XSTATS));
   float ms_slice = time_ms([&] {
     cudaMemsetAsync(xstats, 0, sizeof(double) * I8_XSTATS);
-    i8::slice_x_kernel<32><<<(unsigned)std::min<int64_t>(n_tiles, sms * 8), 256>>>(x, ld, T, n, n_tiles, xblob, xstats);
+    i8::slice_x_kernel<I8_TILE><<<(unsigned)std::min<int64_t>(n_tiles, sms * 8), 8 * I8_TILE>>>(x, ld, T, n, n_tiles, xblob, xstats);
   }, 1);
   CK(cudaGetLastError());
   i8::slice_w_kernel<<<1, 1024>>>(w, n, n, n, wblob);

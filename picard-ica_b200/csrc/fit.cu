@@ -80,6 +80,69 @@ int apply_device(const double* a_host, const double* mean_host, int n_out, int n
   return launches;
 }
 
+// ---- host-side N x N helpers of the whitening refinement (rare path: ill-conditioned data) ------------------------------
+namespace {
+// cyclic Jacobi eigendecomposition of a symmetric matrix (row-major, destroyed): a = V diag(w) V^T, V in columns
+void host_jacobi_eigh(std::vector<double>& a, int n, std::vector<double>& w, std::vector<double>& v) {
+  v.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) v[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i) { diag += a[(size_t)i * n + i] * a[(size_t)i * n + i]; for (int j = i + 1; j < n; ++j) off += a[(size_t)i * n + j] * a[(size_t)i * n + j]; }
+    if (off <= 1e-32 * diag) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = a[(size_t)p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[(size_t)q * n + q] - a[(size_t)p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q];
+          a[(size_t)k * n + p] = c * akp - sn * akq; a[(size_t)k * n + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k];
+          a[(size_t)p * n + k] = c * apk - sn * aqk; a[(size_t)q * n + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q];
+          v[(size_t)k * n + p] = c * vkp - sn * vkq; v[(size_t)k * n + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  w.resize((size_t)n);
+  for (int i = 0; i < n; ++i) w[i] = a[(size_t)i * n + i];
+}
+// one-sided (Hestenes) Jacobi: rotates the COLUMNS of b (n x n, row-major) until they are mutually orthogonal, accumulating the
+// rotations in j (b_in j = b_out): singular values = column norms of b_out, right singular vectors of b_in = columns of j.
+// For b = (well-conditioned) x diag(graded) the small singular values come out with high RELATIVE accuracy (Demmel-Veselic).
+void host_one_sided_jacobi(std::vector<double>& b, int n, std::vector<double>& j) {
+  j.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) j[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        double app = 0, aqq = 0, apq = 0;
+        for (int k = 0; k < n; ++k) { const double x = b[(size_t)k * n + p], y = b[(size_t)k * n + q]; app += x * x; aqq += y * y; apq += x * y; }
+        if (std::fabs(apq) <= 1e-15 * std::sqrt(app * aqq) || apq == 0.0) continue;
+        rotated = true;
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double x = b[(size_t)k * n + p], y = b[(size_t)k * n + q];
+          b[(size_t)k * n + p] = c * x - sn * y; b[(size_t)k * n + q] = sn * x + c * y;
+          const double u = j[(size_t)k * n + p], w2 = j[(size_t)k * n + q];
+          j[(size_t)k * n + p] = c * u - sn * w2; j[(size_t)k * n + q] = sn * u + c * w2;
+        }
+      }
+    if (!rotated) break;
+  }
+}
+}  // namespace
+
 void center_whiten_device(const double* d_x, int nf, int64_t t_local, int64_t ldx, int nc, bool centering, bool whiten,
                           picard_comm* comm, int sm_count, cudaStream_t st, std::vector<double>& mean_host,
                           std::vector<double>& k_host, double t_total, picard_stats_t* stats) {
@@ -132,16 +195,63 @@ void center_whiten_device(const double* d_x, int nf, int64_t t_local, int64_t ld
   PICARD_CUDA(cudaMemcpyAsync(evals.data(), ev.p, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
   PICARD_CUDA(cudaMemcpyAsync(U.data(), V.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
   PICARD_CUDA(cudaStreamSynchronize(st));
-  // singular values descending = sqrt of eigenvalues descending (dgesvd order); min over the kept ones (whitening.rs:72-79)
-  // The eigenvalues of the Gram matrix carry rounding noise ~eps * lambda_max, so singular values below ~1e-7 sigma_max
-  // cannot be told from zero (the reference's SVD resolves them down to its absolute 1e-10): they are reported as singular.
-  const double noise_floor = 1e-14 * std::fmax(evals[nf - 1], 0.0);
+  // singular values descending = sqrt of eigenvalues descending (dgesvd order).
+  // The eigenvalues of the Gram matrix carry rounding noise ~eps * lambda_max, so singular values below ~1e-3 sigma_max come out
+  // with a relative error above 1e-10 and those below ~1e-7 sigma_max cannot be told from zero, while the reference's SVD of X
+  // itself resolves them down to its absolute threshold of 1e-10 (whitening.rs:61-79).  When the kept spectrum reaches that
+  // range the decomposition is REFINED (two more N x T passes, rare path):
+  //   K1 = S1^-1 U^T from the first eigh (tiny / negative eigenvalues floored) ; C2 = K1 C K1^T accumulated from the data in f64
+  //   (= I where the first stage was right) ; C2 = V D V^T (host Jacobi) ; then C = M M^T with M = U S1 V D^1/2, and the SVD of M --
+  //   one-sided Jacobi on (D^1/2 V^T) S1, a well-conditioned matrix times a graded diagonal: high RELATIVE accuracy for the small
+  //   singular values -- gives U and sigma of X_c as an SVD of X_c would.
+  const double lam_max = std::fmax(evals[nf - 1], 0.0);
+  if (nc >= 1 && evals[nf - nc] < 1e-6 * lam_max && lam_max > 0.0) {
+    const double floor_l = 4.0 * 2.220446049250313e-16 * lam_max;
+    std::vector<double> s1((size_t)nf), k1(nn);
+    for (int i = 0; i < nf; ++i) {
+      s1[i] = std::sqrt(std::fmax(evals[i], floor_l));
+      for (int j = 0; j < nf; ++j) k1[(size_t)i * nf + j] = U[(size_t)j * nf + i] / s1[i];
+    }
+    const int64_t ldz = round_up(t_local, 16);
+    DevBuf<double> z((size_t)nf * ldz);
+    stats->kernel_launches += apply_device(k1.data(), centering ? mean_host.data() : nullptr, nf, nf, d_x, ldx, z.p, ldz, t_local, sm_count, st);
+    PassLaunch L2 = L;
+    L2.d_x = z.p; L2.ldx = ldz; L2.d_bias = nullptr;
+    stats->kernel_launches += launch_pass(L2);
+    comm_allreduce_sum(comm, mom.p + mom_off_gr(nf), nn, st);
+    std::vector<double> c2(nn), vd, V2;
+    PICARD_CUDA(cudaMemcpyAsync(c2.data(), mom.p + mom_off_gr(nf), sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
+    PICARD_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < nf; ++i)
+      for (int j = i + 1; j < nf; ++j) { const double a = 0.5 * (c2[(size_t)i * nf + j] + c2[(size_t)j * nf + i]); c2[(size_t)i * nf + j] = c2[(size_t)j * nf + i] = a; }
+    host_jacobi_eigh(c2, nf, vd, V2);
+    // B = (D^1/2 V^T) S1 : b[i][j] = sqrt(d_i) V2[j][i] s1[j]
+    std::vector<double> b(nn), jrot;
+    for (int i = 0; i < nf; ++i) {
+      const double sd_i = std::sqrt(std::fmax(vd[i], 0.0));
+      for (int j = 0; j < nf; ++j) b[(size_t)i * nf + j] = sd_i * V2[(size_t)j * nf + i] * s1[j];
+    }
+    host_one_sided_jacobi(b, nf, jrot);
+    // sigma_j^2 = squared norm of column j of the rotated B ; left singular vectors of X_c = U jrot ; sort ascending like eigh
+    std::vector<double> lam((size_t)nf), Unew(nn);
+    for (int j = 0; j < nf; ++j) { double sj = 0; for (int k = 0; k < nf; ++k) sj += b[(size_t)k * nf + j] * b[(size_t)k * nf + j]; lam[j] = sj; }
+    for (int i = 0; i < nf; ++i)
+      for (int j = 0; j < nf; ++j) { double acc = 0; for (int k = 0; k < nf; ++k) acc += U[(size_t)i * nf + k] * jrot[(size_t)k * nf + j]; Unew[(size_t)i * nf + j] = acc; }
+    std::vector<int> order((size_t)nf);
+    for (int i = 0; i < nf; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int c) { return lam[a] < lam[c]; });
+    for (int jn = 0; jn < nf; ++jn) {
+      evals[jn] = lam[order[jn]];
+      for (int i = 0; i < nf; ++i) U[(size_t)i * nf + jn] = Unew[(size_t)i * nf + order[jn]];
+    }
+    mark("whiten: refinement (ill-conditioned data)");
+  }
   double min_sv = INFINITY;
   for (int i = 0; i < nc; ++i) {
     const double ev = evals[nf - 1 - i];
-    min_sv = std::fmin(min_sv, ev > noise_floor ? std::sqrt(ev) : 0.0);
+    min_sv = std::fmin(min_sv, ev > 0.0 ? std::sqrt(ev) : 0.0);
   }
-  if (!(min_sv >= 1e-10)) throw Error(PICARD_SINGULAR_MATRIX, "Singular matrix encountered during computation");
+  if (!(min_sv >= 1e-10)) throw Error(PICARD_SINGULAR_MATRIX, "Singular matrix encountered during computation");  // whitening.rs:72-79
   const double scale = std::sqrt(t_total);  // whitening.rs:83
   k_host.assign((size_t)nc * nf, 0.0);
   for (int i = 0; i < nc; ++i) {

@@ -215,13 +215,16 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
         if (TRACE && blockIdx.x == 0 && it < I8_TRACE_SLOTS) trace[it * 8 + 1] = clock64();
         const uint32_t a0 = smem_u32(osm + (size_t)sl * G::SLOT_BYTES);
         const uint32_t b0 = a0 + S * G::A_DIGIT_BYTES;
+        // Y digit pa against psi digits qb .. qb + m - 1 in ONE MMA of N = 64 m columns (the psi digits are adjacent 64-row blocks
+        // of the slot, the level accumulators adjacent 64-column blocks): 8 MMAs per tile instead of 21, N up to 256.  Digit 0 of Y
+        // touches every level: after a flush its MMAs re-initialise all accumulators.
 #pragma unroll
-        for (int d = 0; d < S; ++d) {
+        for (int pa = 0; pa < S; ++pa) {
 #pragma unroll
-          for (int pa = 0; pa <= d; ++pa) {
-            const int qb = d - pa;
-            umma_i8_ss(tmem + (uint32_t)(d * G::NB), make_desc_k32<LAYOUT>(a0 + pa * G::A_DIGIT_BYTES), make_desc_k32<LAYOUT>(b0 + qb * G::B_DIGIT_BYTES),
-                       G::IDESC, (since_flush > 0 || pa > 0) ? 1u : 0u);
+          for (int qb = 0; qb < S - pa; qb += 4) {
+            const int m = (S - pa - qb) < 4 ? (S - pa - qb) : 4;
+            umma_i8_ss(tmem + (uint32_t)((pa + qb) * G::NB), make_desc_k32<LAYOUT>(a0 + pa * G::A_DIGIT_BYTES),
+                       make_desc_k32<LAYOUT>(b0 + qb * G::B_DIGIT_BYTES), make_idesc(m * G::NB), (since_flush > 0 || pa > 0) ? 1u : 0u);
           }
         }
         umma_commit(&o_empty[sl]);

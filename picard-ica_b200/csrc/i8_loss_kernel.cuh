@@ -10,7 +10,7 @@
 //
 // loss_i8_kernel, one CTA per SM, 18 warps:
 //   warp 16 (one lane) : bulk copies of the x1 tiles into a 2-stage ring (mbarrier transaction bytes)
-//   warp 17 (one lane) : per tile 21 products x 4 K-steps = 84 tcgen05.mma (128 x NT x 32, kind::i8).  The A operand (the W'
+//   warp 17 (one lane) : per tile 21 products x 4 K-steps, several products per tcgen05.mma (kind::i8, N up to 256).  The A operand (the W'
 //                        digits, 6 x 32 columns) lives in TENSOR MEMORY next to the 6 level accumulators (6 x NT columns), so
 //                        the MMAs only read the B operand from shared memory; tcgen05.commit releases the ring stage and
 //                        publishes the accumulators
@@ -242,17 +242,24 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
         ptx::mbar_wait(acc_empty, (uint32_t)((it & 1) ^ 1));  // the epilogue has read tile it - 1 back (first tile: passes)
         tc_fence_after();
         if (TRACE && blockIdx.x == 0 && it < I8_TRACE_SLOTS) trace[it * 8 + 2] = clock64();
+        // One MMA covers several digit products at once: the digits of a tile are adjacent blocks of NT rows in shared memory and
+        // the level accumulators adjacent blocks of NT columns in tensor memory, so W' digit p against x digits q .. q + m - 1 is ONE
+        // 128 x (m NT) x 32 MMA writing levels p + q .. p + q + m - 1 (N up to 256: the INT8 tensor rate needs N >= 128,
+        // profiles/microbench/pipe_probe_r02.jsonl).  Digit 0 of W' goes first: it touches every level, so its MMAs of the first
+        // K-step initialise all accumulators and everything else accumulates.
+        constexpr int MAXD = 256 / NT;  // digits per MMA
 #pragma unroll
-        for (int d = 0; d < S; ++d) {
-          const uint32_t tacc = tmem + (uint32_t)(d * NT);
+        for (int k = 0; k < KP / 32; ++k) {
 #pragma unroll
-          for (int pa = 0; pa <= d; ++pa) {
-            const int qb = d - pa;
+          for (int pa = 0; pa < S; ++pa) {
 #pragma unroll
-            for (int k = 0; k < KP / 32; ++k) {
+            for (int qb = 0; qb < S - pa; qb += MAXD) {
+              const int m = (S - pa - qb) < MAXD ? (S - pa - qb) : MAXD;
+              const uint32_t tacc = tmem + (uint32_t)((pa + qb) * NT);
               const uint64_t db = db0 + (uint64_t)((qb * G::SLICE_B_BYTES + k * 32) >> 4);
-              if (pa < G::ATM) umma_i8_ts(tacc, tmem + (uint32_t)(G::TMEM_A + 8 * (4 * pa + k)), db, G::IDESC, (pa > 0 || k > 0) ? 1u : 0u);
-              else umma_i8_ss(tacc, da0 + (uint64_t)(((pa - G::ATM) * SLICE_A_BYTES + k * 32) >> 4), db, G::IDESC, (pa > 0 || k > 0) ? 1u : 0u);
+              const uint32_t acc = (pa > 0 || k > 0) ? 1u : 0u;
+              if (pa < G::ATM) umma_i8_ts(tacc, tmem + (uint32_t)(G::TMEM_A + 8 * (4 * pa + k)), db, make_idesc(m * NT), acc);
+              else umma_i8_ss(tacc, da0 + (uint64_t)(((pa - G::ATM) * SLICE_A_BYTES + k * 32) >> 4), db, make_idesc(m * NT), acc);
             }
           }
         }

@@ -73,11 +73,16 @@ __global__ void __launch_bounds__(1024, 1) probe_kernel(int n_mma, int mma_n, in
       const uint64_t da = make_desc(smem_u32(smem)), db = make_desc(smem_u32(smem + 16384));
       const uint32_t idesc = make_idesc(mma_n);
       const int nacc = a_from_tmem ? (448 / mma_n) : (512 / mma_n);  // rotating accumulators; A (32 columns) at column 448 when in TMEM
+      // issue loop without integer division: 4 K-steps x rotating accumulators, everything but the loop counter precomputed
+      uint32_t dcol[8];
+      for (int a = 0; a < 8; ++a) dcol[a] = tmem + (uint32_t)((a % nacc) * mma_n);
       t0 = clock64();
-      for (int i = 0; i < n_mma; ++i) {
-        const uint32_t d = tmem + (uint32_t)((i % nacc) * mma_n);
-        if (a_from_tmem) umma_i8_ts(d, tmem + 448 + 8 * (i & 3), db + (uint64_t)(((i & 3) * 32) >> 4), idesc, 1u);
-        else umma_i8_ss(d, da + (uint64_t)(((i & 3) * 32) >> 4), db + (uint64_t)(((i & 3) * 32) >> 4), idesc, 1u);
+      for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (a_from_tmem) umma_i8_ts(dcol[u], tmem + 448 + 8 * (u & 3), db + (uint64_t)(((u & 3) * 32) >> 4), idesc, 1u);
+          else umma_i8_ss(dcol[u], da + (uint64_t)(((u & 3) * 32) >> 4), db + (uint64_t)(((u & 3) * 32) >> 4), idesc, 1u);
+        }
       }
       umma_commit(&bar);
       ptx::mbar_wait(&bar, 0);
@@ -124,19 +129,21 @@ int main() {
   CK(cudaMalloc(&d_out, sizeof(long long) * 4 * sms)); CK(cudaMalloc(&d_sink, 64));
   const int NM = 4000;
   // MMA alone: rate vs N and operand source
-  for (int n : {32, 64, 128, 256}) for (int at = 0; at < 2; ++at) run<0>("none", sms, NM, n, at, 0, 16, d_out, d_sink);
+  for (int n : {32, 64, 128, 192, 256}) for (int at = 0; at < 2; ++at) run<0>("none", sms, NM, n, at, 0, 16, d_out, d_sink);
   // ALU alone (16 warps = 4 per sub-partition), sized to last about as long as 4000 MMAs of N = 64 (~220k cycles)
   run<0>("dfma", sms, 0, 64, 0, 3400, 16, d_out, d_sink);
   run<3>("dadd", sms, 0, 64, 0, 3400, 16, d_out, d_sink);
   run<1>("ffma", sms, 0, 64, 0, 6800, 16, d_out, d_sink);
   run<2>("imad", sms, 0, 64, 0, 6800, 16, d_out, d_sink);
   // both together
-  for (int n : {32, 64, 128}) {
+  for (int n : {32, 64, 128, 256}) {
     run<0>("dfma", sms, NM, n, 1, 3400, 16, d_out, d_sink);
     run<1>("ffma", sms, NM, n, 1, 6800, 16, d_out, d_sink);
     run<2>("imad", sms, NM, n, 1, 6800, 16, d_out, d_sink);
   }
   run<0>("dfma", sms, NM, 64, 0, 3400, 16, d_out, d_sink);
+  run<0>("dfma", sms, NM, 256, 0, 3400, 16, d_out, d_sink);
+  run<0>("dfma", sms, NM, 256, 1, 13600, 16, d_out, d_sink);  // FP64 stream as long as the MMA stream
   run<0>("dfma", sms, NM, 64, 1, 850, 16, d_out, d_sink);   // light FP64 load (25 % of the pipe)
   run<0>("dfma", sms, NM, 64, 1, 3400, 4, d_out, d_sink);   // one warp per sub-partition
   printf("{\"done\": 1}\n");

@@ -75,7 +75,7 @@ const char* picard_status_string(int status) {
   }
 }
 
-void picard_release_cache(void) { dev_cache_release(); }
+void picard_release_cache(void) { dev_cache_release(); result_arena_free(); }
 
 void picard_config_default(picard_config_t* cfg) { if (cfg) config_default(cfg); }
 
@@ -118,7 +118,8 @@ int picard_transform(const double* x, int64_t n_features, int64_t n_samples, int
 
 void picard_result_free(picard_result_t* r) {
   if (!r) return;
-  free(r->whitening); free(r->unmixing); free(r->sources); free(r->mean); free(r->signs);
+  free(r->whitening); free(r->unmixing); free(r->mean); free(r->signs);
+  if (!result_arena_release(r->sources)) free(r->sources);  // a large `sources` lives in the pinned result arena (fit.cu)
   r->whitening = r->unmixing = r->sources = r->mean = r->signs = nullptr;
 }
 

@@ -154,13 +154,15 @@ CoreSolver::CoreSolver(const double* d_x, int n, int64_t t_local, int64_t ldx, c
   if (!(cfg.flags & PICARD_FLAG_NO_Y_STORE)) {
     // one extra N x T buffer: an accepted loss-only try leaves its Y' here, so the next gradient pass skips W X.
     // Not having the memory is not an error: the gradient pass then recomputes from X.
-    try { ybuf_.alloc((size_t)n * (size_t)ldx_); } catch (const Error&) { cudaGetLastError(); ybuf_.release(); }
+    ldy_ = round_up(t_local_, 64);  // its own leading dimension: whole 64-sample tiles of the INT8 LOSS pass stay in bounds
+    try { ybuf_.alloc((size_t)n * (size_t)ldy_); } catch (const Error&) { cudaGetLastError(); ybuf_.release(); }
   }
   PICARD_CUDA(cudaEventCreate(&ev_a_));
   PICARD_CUDA(cudaEventCreate(&ev_b_));
   PICARD_CUDA(cudaEventCreate(&ev_run0_));
   PICARD_CUDA(cudaEventCreate(&ev_run1_));
   memset(&stats_, 0, sizeof stats_);
+  memset(sc_host_.p, 0, sizeof(CoreScalars));
   reset();
 }
 
@@ -198,12 +200,13 @@ bool CoreSolver::i8_prepare() {
   if (!forced && !cov_identity_) return false;
   try {
     xs8_.alloc(i8_blob_bytes(t_local_));
-    wblob8_.alloc((size_t)I8_WBLOB_BYTES);
+    i8_counter_.alloc(2);
+    PICARD_CUDA(cudaMemsetAsync(i8_counter_.p, 0, 2 * sizeof(unsigned int), st_));
     xstats_.alloc((size_t)I8_XSTATS);
     rowexp_.alloc(128);
   } catch (const Error&) {  // no memory for the digit image: the FP64 kernels need none
     cudaGetLastError();
-    xs8_.release(); wblob8_.release(); xstats_.release(); rowexp_.release();
+    xs8_.release(); i8_counter_.release(); xstats_.release(); rowexp_.release();
     stats_.i8_fallbacks = 1;
     return false;
   }
@@ -216,7 +219,7 @@ bool CoreSolver::i8_prepare() {
   const double mean_bound = hs[0] / (double)t_local_;
   stats_.i8_range = min_ms > 0.0 ? mean_bound / std::sqrt(min_ms) : INFINITY;
   if (!forced && !(stats_.i8_range <= 64.0)) {
-    xs8_.release(); wblob8_.release();
+    xs8_.release();
     stats_.i8_fallbacks = 1;
     return false;
   }
@@ -224,13 +227,14 @@ bool CoreSolver::i8_prepare() {
   return true;
 }
 
-void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, double alpha, double* d_mom, bool store_y) {
+bool CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, double alpha, double* d_mom, bool store_y, int finish_which,
+                           const double* finish_signs) {
   PassLaunch L;
-  L.d_x = (mode == PASS_GRADY) ? ybuf_.p : d_x_; L.ldx = ldx_; L.t_local = t_local_; L.n_in = dims_.n; L.n_out = dims_.n;
+  L.d_x = (mode == PASS_GRADY) ? ybuf_.p : d_x_; L.ldx = (mode == PASS_GRADY) ? ldy_ : ldx_; L.t_local = t_local_; L.n_in = dims_.n; L.n_out = dims_.n;
   L.d_w = d_w; L.ldw = dims_.n; L.d_bias = nullptr; L.dens = dens; L.alpha = alpha; L.mode = mode; L.want_h = want_h;
   L.d_partial = partial_.p; L.d_mom = d_mom; L.sm_count = sm_count_; L.stream = st_;
   const bool store = store_y && mode == PASS_LOSS && ybuf_.p != nullptr;
-  L.d_out = store ? ybuf_.p : nullptr; L.ld_out = store ? ldx_ : 0;
+  L.d_out = store ? ybuf_.p : nullptr; L.ld_out = store ? ldy_ : 0;
   if (mode == PASS_LOSS) ybuf_valid_ = store;
   // INT8 tensor-core engines (i8_loss.cu / i8_grad.cu) for whitened problems with 64 < N <= 128
   const bool use_i8 = mode == PASS_LOSS && dens != DENS_LINEAR && i8_prepare();
@@ -240,9 +244,23 @@ void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
   else if (mode == PASS_GRAD) stats_.grad_passes++;
   else if (mode == PASS_GRADY) stats_.grady_passes++;
   else stats_.loss_passes++;
+  resolve_pass_time();
   PICARD_CUDA(cudaEventRecord(ev_a_, st_));
-  if (use_i8) { stats_.kernel_launches += launch_loss_i8(L, xs8_.p, wblob8_.p); stats_.i8_loss_passes++; }
-  else if (use_i8_grad) { stats_.kernel_launches += launch_grad_i8(L, rowexp_.p); stats_.i8_grad_passes++; }
+  bool finished = false;
+  if (use_i8) {
+    // one launch: W' digits, streaming, deterministic reduction of the partials [, on a single GPU: loss + accept flag + publish]
+    const bool single = !(comm_ && comm_size(comm_) > 1);
+    I8LossFinish fin;
+    fin.counter = i8_counter_.p; fin.counter_total = &i8_counter_total_[0];
+    if (finish_which >= 0 && single) {
+      fin.finish = 1; fin.which = finish_which; fin.dims = &dims_; fin.signs = finish_signs; fin.sc = sc_dev_.p; fin.sc_map = sc_host_.p;
+      fin.seq = next_seq();
+      finished = true;
+    }
+    stats_.kernel_launches += launch_loss_i8(L, xs8_.p, fin);
+    stats_.i8_loss_passes++;
+  }
+  else if (use_i8_grad) { stats_.kernel_launches += launch_grad_i8(L, rowexp_.p, i8_counter_.p + 1, &i8_counter_total_[1]); stats_.i8_grad_passes++; }
   else stats_.kernel_launches += launch_pass(L);
   PICARD_CUDA(cudaEventRecord(ev_b_, st_));
   // one NCCL allreduce of exactly what this pass produced
@@ -255,22 +273,46 @@ void CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
     else comm_allreduce_sum2(comm_, d_mom, nn + 2 * (size_t)n, want_h ? d_mom + mom_off_hr(n) : nullptr, want_h ? nn : 0, st_);
   }
   last_pass_mode_ = mode;
+  return finished;
 }
 
-void CoreSolver::pass(const double* d_w, int mode, double* d_mom) {
-  eval_pass(d_w, mode, need_h_, dens_, alpha_, d_mom, /*store_y=*/true);  // LOSS mode: want_h = the Sq row sums only
+bool CoreSolver::pass(const double* d_w, int mode, double* d_mom, int finish_which, const double* finish_signs) {
+  return eval_pass(d_w, mode, need_h_, dens_, alpha_, d_mom, /*store_y=*/true, finish_which, finish_signs);  // LOSS mode: want_h = the Sq row sums only
 }
 
+// The kernel that finalised the scalars (loss_kernel / front_kernel, launched with next_seq()) has written them into the pinned
+// host mirror and then the sequence number: spin on it instead of a D2H copy + stream synchronisation.
 void CoreSolver::fetch_scalars() {
-  PICARD_CUDA(cudaMemcpyAsync(sc_host_.p, sc_dev_.p, sizeof(CoreScalars), cudaMemcpyDeviceToHost, st_));
-  PICARD_CUDA(cudaStreamSynchronize(st_));
-  // the last pass has certainly finished: account its device time
+  volatile CoreScalars* h = sc_host_.p;
+  for (uint64_t spins = 1; h->seq != seq_; ++spins) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 0x3FFF) == 0) {  // a faulting kernel must not leave the host spinning forever
+      const cudaError_t e = cudaStreamQuery(st_);
+      if (e != cudaSuccess && e != cudaErrorNotReady)
+        throw Error(PICARD_COMPUTATION_ERROR, std::string("Computation error: CUDA failure '") + cudaGetErrorString(e) + "' in the core loop");
+      if (e == cudaSuccess && h->seq != seq_) {  // stream idle: the publishing store is visible by now (system-scope fence)
+        PICARD_CUDA(cudaStreamSynchronize(st_));
+        if (h->seq != seq_) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: the core loop's scalars were not published");
+      }
+    }
+  }
+}
+
+// Device time of the last pass kernel (events around its launch) goes to the statistics.  The fused LOSS kernel publishes its
+// scalars before it retires, so the closing event may still be pending when the host has its answer: the time is resolved lazily,
+// at the next pass launch or when the loop returns (by then the event has completed; no extra wait on the critical path).
+void CoreSolver::resolve_pass_time() {
+  if (last_pass_mode_ < 0) return;
   float ms = 0.f;
-  if (last_pass_mode_ >= 0 && cudaEventElapsedTime(&ms, ev_a_, ev_b_) == cudaSuccess) {
+  if (cudaEventSynchronize(ev_b_) == cudaSuccess && cudaEventElapsedTime(&ms, ev_a_, ev_b_) == cudaSuccess) {
     if (last_pass_mode_ == PASS_FUSED) stats_.pass_ms_fused += ms;
     else if (last_pass_mode_ == PASS_GRAD) stats_.pass_ms_grad += ms;
     else if (last_pass_mode_ == PASS_LOSS) stats_.pass_ms_loss += ms;
     else if (last_pass_mode_ == PASS_GRADY) stats_.pass_ms_grady += ms;
+  } else {
+    cudaGetLastError();
   }
   last_pass_mode_ = -1;
 }
@@ -305,9 +347,9 @@ void CoreSolver::try_point(double alpha, bool speculate, int try_index, int trie
     stats_.kernel_launches += small::sln_det(Wt_, n, lu_work_, mom_trial_ + mom_size(n), st_);
   static double host_enq_ms = 0.0;
   if (prof) { host_enq_ms += trace_now_ms() - w0; cudaEventRecord(pe[1], st_); }
-  pass(w_try_, speculate ? PASS_FUSED : PASS_LOSS, mom_trial_);                                   // core.rs:124,127
+  const bool finished = pass(w_try_, speculate ? PASS_FUSED : PASS_LOSS, mom_trial_, 0, signs_);  // core.rs:124,127
   if (prof) cudaEventRecord(pe[2], st_);
-  stats_.kernel_launches += small::loss_from_moments(dims_, mom_trial_, signs_, sc_dev_.p, 0, st_);
+  if (!finished) stats_.kernel_launches += small::loss_from_moments(dims_, mom_trial_, signs_, sc_dev_.p, 0, st_, sc_host_.p, next_seq());
   if (prof) cudaEventRecord(pe[3], st_);
   fetch_scalars();
   if (prof) {
@@ -332,9 +374,9 @@ int64_t CoreSolver::run(int64_t max_new) {
   if (!started_) {
     // initial loss with signs = 1 (core.rs:185-194, quirk Q1); the same pass already yields the first gradient
     if (!dims_.ortho) stats_.kernel_launches += small::sln_det(W_, n, lu_work_, mom_cur_ + mom_size(n), st_);
-    pass(W_, no_spec ? PASS_LOSS : PASS_FUSED, mom_cur_);
+    const bool finished = pass(W_, no_spec ? PASS_LOSS : PASS_FUSED, mom_cur_, 1, nullptr);
     have_cur_ = !no_spec;
-    stats_.kernel_launches += small::loss_from_moments(dims_, mom_cur_, nullptr, sc_dev_.p, 1, st_);
+    if (!finished) stats_.kernel_launches += small::loss_from_moments(dims_, mom_cur_, nullptr, sc_dev_.p, 1, st_, sc_host_.p, next_seq());
     fetch_scalars();
     if (sc_host_.p->loss_singular) throw Error(PICARD_SINGULAR_MATRIX, "Singular matrix encountered during computation");
     current_loss_ = sc_host_.p->current_loss;
@@ -355,6 +397,7 @@ int64_t CoreSolver::run(int64_t max_new) {
     fa.d = dims_; fa.mom = mom_cur_; fa.C = C_; fa.G = G_; fa.Gtmp = Gtmp_; fa.G_old = Gold_; fa.H = H_; fa.hoff = hoff_;
     fa.signs = signs_; fa.old_signs = old_signs_; fa.S_prev = Sprev_; fa.mem_s = mem_s_; fa.mem_y = mem_y_; fa.mem_r = mem_r_;
     fa.q = q_; fa.D = D_; fa.sc = sc_dev_.p; fa.first_iter = (iter_ == 0) ? 1 : 0; fa.do_lbfgs = 1;
+    fa.sc_map = sc_host_.p; fa.seq = next_seq();
     stats_.kernel_launches += small::iteration_front(fa, st_);
     fetch_scalars();
     gradient_norm_ = sc_host_.p->gradient_norm;
@@ -413,6 +456,7 @@ int64_t CoreSolver::run(int64_t max_new) {
   }
   PICARD_CUDA(cudaEventRecord(ev_run1_, st_));
   PICARD_CUDA(cudaStreamSynchronize(st_));
+  resolve_pass_time();
   float ms = 0.f;
   PICARD_CUDA(cudaEventElapsedTime(&ms, ev_run0_, ev_run1_));
   stats_.core_ms += ms;
@@ -499,7 +543,7 @@ void CoreSolver::hook_point(const double* w_host, const double* c_host, const do
     PICARD_CUDA(cudaMemcpyAsync(q_, loss_signs_host, sizeof(double) * n, cudaMemcpyHostToDevice, st_));
     ls = q_;
   }
-  stats_.kernel_launches += small::loss_from_moments(dims_, mom_cur_, ls, sc_dev_.p, 1, st_);
+  stats_.kernel_launches += small::loss_from_moments(dims_, mom_cur_, ls, sc_dev_.p, 1, st_, sc_host_.p, next_seq());
   fetch_scalars();
   auto get = [&](double* dst, const double* src, size_t cnt) {
     if (dst) PICARD_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st_));

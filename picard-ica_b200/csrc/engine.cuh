@@ -33,6 +33,9 @@ void trace_slow(const char* what, size_t bytes, double t0_ms);
 void* dev_alloc(size_t bytes, size_t* capacity);
 void dev_free(void* p, size_t capacity);
 void dev_cache_release();  // return every cached block to the driver
+// pinned arena of large `sources` results (fit.cu)
+bool result_arena_release(double* p);  // true if p was the arena: it is free for the next fit
+void result_arena_free();
 
 // ---- RAII device / pinned buffers
 template <typename T>
@@ -109,15 +112,19 @@ class CoreSolver {
   int n() const { return dims_.n; }
 
   // one evaluation of the pass at an arbitrary W into a moment buffer (test hook + internal use)
-  void eval_pass(const double* d_w, int mode, bool want_h, int dens, double alpha, double* d_mom, bool store_y = false);
+  // Returns true when the loss of the point was computed and published inside the pass kernel (finish_which >= 0 asked for it
+  // and the engine supports it): the caller then skips loss_from_moments and goes straight to fetch_scalars().
+  bool eval_pass(const double* d_w, int mode, bool want_h, int dens, double alpha, double* d_mom, bool store_y = false,
+                 int finish_which = -1, const double* finish_signs = nullptr);
   // test hooks (picard_eval_moments / picard_eval_point): host in, host out
   void hook_moments(const double* w_host, int mode, bool want_h, double* gr, double* sd, double* hr, double* sq, double* lrow);
   void hook_point(const double* w_host, const double* c_host, const double* old_signs_host, const double* loss_signs_host,
                   double* g, double* h, double* hoff, double* signs, int32_t* sign_change, double* gradient_norm, double* loss);
 
  private:
-  void pass(const double* d_w, int mode, double* d_mom);
+  bool pass(const double* d_w, int mode, double* d_mom, int finish_which = -1, const double* finish_signs = nullptr);
   void fetch_scalars();
+  void resolve_pass_time();
   void try_point(double alpha, bool speculate, int try_index, int tries_planned);
 
   CoreDims dims_;
@@ -139,14 +146,19 @@ class CoreSolver {
   double* w_try_ = nullptr;  // W' of the last evaluated try
   DevBuf<double> ybuf_;    // Y' of the last loss-only try (n x ldx_), empty when PICARD_FLAG_NO_Y_STORE or out of memory
   bool ybuf_valid_ = false;
+  int64_t ldy_ = 0;        // leading dimension of ybuf_
   // INT8 tensor-core passes (i8_loss.cu, i8_grad.cu): decided once per solver at the first LOSS pass (i8_prepare)
-  DevBuf<uint8_t> xs8_, wblob8_;  // digit image of x1 and of the trial W
+  DevBuf<uint8_t> xs8_;           // digit image of x1
+  DevBuf<unsigned int> i8_counter_;  // [0] LOSS pass, [1] gradient pass: CTAs counted by the kernels' tails
+  unsigned int i8_counter_total_[2] = {0, 0};
   DevBuf<double> xstats_;         // statistics of x1 gathered while slicing (I8_XSTATS)
   DevBuf<int> rowexp_;            // exponents of the rows of the stored Y (gradient pass)
   int i8_state_ = 0;              // 0 = undecided, 1 = in use, -1 = not used
   bool i8_prepare();
   DevBuf<CoreScalars> sc_dev_;
-  PinnedBuf<CoreScalars> sc_host_;
+  PinnedBuf<CoreScalars> sc_host_;   // pinned mirror, also written by the device (publish_scalars)
+  unsigned long long seq_ = 0;        // sequence number of the last publishing kernel launched
+  unsigned long long next_seq() { return ++seq_; }
   // views into store_
   double *W_, *Wt_, *M_, *D_, *C_, *G_, *Gtmp_, *Gold_, *H_, *hoff_, *signs_, *old_signs_, *Sprev_, *q_;
   double *mem_s_, *mem_y_, *mem_r_;

@@ -283,11 +283,12 @@ constexpr size_t kStageBytes = (size_t)16 << 20;
 constexpr int kMaxWorkers = 8;
 }  // namespace
 
+static bool result_is_pinned(const double* p);
 static void d2h_pipelined(double* dst, const double* src_dev, int64_t src_ld, int64_t rows, int64_t cols, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return;
   const size_t row_bytes = sizeof(double) * (size_t)cols;
   const size_t total = row_bytes * (size_t)rows;
-  if (total < ((size_t)32 << 20)) {  // small: one plain copy
+  if (total < ((size_t)32 << 20) || result_is_pinned(dst)) {  // small, or a pinned destination: one plain copy (DMA at PCIe speed)
     PICARD_CUDA(cudaMemcpy2DAsync(dst, row_bytes, src_dev, sizeof(double) * src_ld, row_bytes, rows, cudaMemcpyDeviceToHost, st));
     PICARD_CUDA(cudaStreamSynchronize(st));
     return;
@@ -365,8 +366,58 @@ static void d2h_pipelined(double* dst, const double* src_dev, int64_t src_ld, in
                                                              cudaGetErrorString(cudaGetLastError()));
 }
 
-// Result buffers are released with free() (picard_result_free).
+// Small result buffers are released with free() (picard_result_free).  A LARGE `sources` result (>= 256 MB: 10 GB at c3) comes from
+// a process-wide PINNED arena instead: the device-to-host copy then is one DMA at PCIe speed straight into the result (no staging
+// memcpy, no first-touch page faults), and the time does not depend on what the host's page cache is doing.  Page-locking is slow
+// (seconds for 10 GB), so the arena is allocated once, kept, and reused by later fits; while a result still owns it (or the
+// allocation fails) fits fall back to malloc + the staged copy.  picard_result_free() returns it, picard_release_cache() frees it.
+namespace {
+struct ResultArena {
+  std::mutex mu;
+  double* base = nullptr;
+  size_t bytes = 0;
+  bool busy = false;
+};
+ResultArena g_result_arena;
+constexpr size_t kArenaMinBytes = (size_t)256 << 20;
+}  // namespace
+
+static double* result_arena_acquire(size_t count) {
+  const size_t bytes = sizeof(double) * count;
+  if (bytes < kArenaMinBytes || getenv("PICARD_NO_PINNED_RESULT") != nullptr) return nullptr;
+  std::lock_guard<std::mutex> lk(g_result_arena.mu);
+  if (g_result_arena.busy) return nullptr;
+  if (g_result_arena.bytes < bytes) {
+    if (g_result_arena.base) cudaFreeHost(g_result_arena.base);
+    g_result_arena.base = nullptr; g_result_arena.bytes = 0;
+    const size_t want = (bytes + ((size_t)64 << 20) - 1) & ~(((size_t)64 << 20) - 1);
+    const double t0 = trace_now_ms();
+    if (cudaHostAlloc((void**)&g_result_arena.base, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); g_result_arena.base = nullptr; return nullptr; }
+    trace_slow("cudaHostAlloc (result arena)", want, t0);
+    g_result_arena.bytes = want;
+  }
+  g_result_arena.busy = true;
+  return g_result_arena.base;
+}
+bool result_arena_release(double* p) {  // true: p was the arena (now free for the next fit)
+  if (!p) return false;
+  std::lock_guard<std::mutex> lk(g_result_arena.mu);
+  if (p != g_result_arena.base) return false;
+  g_result_arena.busy = false;
+  return true;
+}
+void result_arena_free() {
+  std::lock_guard<std::mutex> lk(g_result_arena.mu);
+  if (g_result_arena.base && !g_result_arena.busy) { cudaFreeHost(g_result_arena.base); g_result_arena.base = nullptr; g_result_arena.bytes = 0; }
+}
+static bool result_is_pinned(const double* p) {
+  std::lock_guard<std::mutex> lk(g_result_arena.mu);
+  return p != nullptr && p == g_result_arena.base;
+}
+static void free_result(double* p) { if (!result_arena_release(p)) free(p); }
+
 static double* alloc_result(size_t count) {
+  if (double* a = result_arena_acquire(count)) return a;
   void* p = malloc(sizeof(double) * (count ? count : 1));
   if (!p) throw Error(PICARD_COMPUTATION_ERROR, "Computation error: out of host memory");
   return (double*)p;
@@ -379,7 +430,7 @@ struct Prefault {
   std::vector<std::thread> th;
   void start(double* p, size_t count) {
     const size_t bytes = sizeof(double) * count;
-    if (bytes < ((size_t)64 << 20)) return;
+    if (bytes < ((size_t)64 << 20) || result_is_pinned(p)) return;  // the pinned arena is resident already
     unsigned hw = std::thread::hardware_concurrency();
     const int n = (int)std::max(1u, std::min(16u, hw ? hw / 2 : 2u));
     unsigned char* base = reinterpret_cast<unsigned char*>(p);
@@ -400,7 +451,7 @@ struct PendingResult {
   double* p = nullptr;
   size_t count = 0;
   Prefault pf;
-  void drop() { pf.join(); free(p); p = nullptr; count = 0; }
+  void drop() { pf.join(); free_result(p); p = nullptr; count = 0; }
 };
 static thread_local PendingResult* g_pending_result = nullptr;
 
@@ -537,7 +588,7 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   stats.preprocess_ms = pre_ms;
 
   const bool keep_dev = (cfg.flags & PICARD_FLAG_KEEP_SOURCES_ON_DEVICE) != 0;
-  struct HostBuf { double* p = nullptr; ~HostBuf() { free(p); } double* release() { double* q = p; p = nullptr; return q; } } src_guard;
+  struct HostBuf { double* p = nullptr; ~HostBuf() { free_result(p); } double* release() { double* q = p; p = nullptr; return q; } } src_guard;
   Prefault prefault;
   if (!keep_dev) {
     PendingResult* pr = g_pending_result;

@@ -142,6 +142,11 @@ struct GradParams {
   const int* rowexp;     // n ints: e_j with 1.008 |y_jt| < 2^e_j
   int psi_exp;
   double* partial;       // [gridDim.x][rb_partial_size(64, 128, true, false)]
+  // tail (optional): every CTA waits until all partials are published (device-wide counter; the CTAs are co-resident: cooperative
+  // launch, one CTA per SM) and then sums its slice of [Gr | Sd] over the tile groups in a fixed order into the moment buffer
+  unsigned int* counter; // nullptr: no tail (the host launches the reduction)
+  unsigned int target;
+  double* mom;
 };
 
 #ifndef I8_TRACE_SLOTS
@@ -376,9 +381,35 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
       rs[2 * G::NB + tid] = 0.0;
     }
   }
+  __threadfence();  // this CTA's partial is visible device-wide before the CTA is counted
   tc_fence_before();
   __syncthreads();
   if (warp == G::NCW + 1) tmem_dealloc512(tmem);
+  if (p.counter != nullptr) {
+    if (tid == 0) {
+      atomicAdd(p.counter, 1u);
+      while ((int)(*reinterpret_cast<volatile unsigned int*>(p.counter) - p.target) < 0) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+    const int n = p.n, nn = n * n, total = nn + n;
+    const int chunk = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = (int)blockIdx.x * chunk, hi = lo + chunk < total ? lo + chunk : total;
+    constexpr int PSZ = G::NB * G::MA + 3 * G::NB;
+    for (int e = lo + tid; e < hi; e += G::NTHREADS) {
+      const int row = e < nn ? e / n : e - nn;                       // row of Gr / entry of Sd
+      const int src = e < nn ? (row & 63) * G::MA + (e - row * n) : G::NB * G::MA + (row & 63);
+      const double* pp = p.partial + (size_t)(row >> 6) * PSZ + src; // CTA 2 tg + half
+      double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      int k = 0;
+      for (; k + 8 <= n_tg; k += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += __ldcg(pp + (size_t)(k + u) * 2 * PSZ);
+      }
+      for (int u = 0; k < n_tg; ++k, ++u) acc[u] += __ldcg(pp + (size_t)k * 2 * PSZ);
+      p.mom[(e < nn ? mom_off_gr(n) + e : mom_off_sd(n) + row)] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    }
+  }
 }
 
 // e_j = bound_exponent(|w_j|_2 * max_t |x_t|_2): one warp per row

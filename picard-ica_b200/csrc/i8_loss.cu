@@ -26,10 +26,11 @@ int i8_slice_x(const double* d_x, int64_t ldx, int64_t t_local, int n, uint8_t* 
 }
 
 template <int DENS, bool WANT_SQ>
-static int launch_loss_i8_one(const PassLaunch& L, const uint8_t* xblob, uint8_t* wblob) {
+static int launch_loss_i8_one(const PassLaunch& L, const uint8_t* xblob, const I8LossFinish& fin) {
   using G = i8::LossGeom<I8_TILE>;
   auto kern = i8::loss_i8_kernel<DENS, WANT_SQ, I8_TILE, 0>;
-  const CUtensorMap tmap_out = L.d_out != nullptr ? make_tmap_box(L.d_out, L.ld_out, L.t_local, L.n_out, G::CPT, 32, false) : CUtensorMap{};
+  if (L.d_out != nullptr && ((L.ld_out % I8_TILE) != 0 || (reinterpret_cast<uintptr_t>(L.d_out) & 15) != 0))
+    throw Error(PICARD_COMPUTATION_ERROR, "Computation error: the Y store of the INT8 LOSS pass needs a 16-byte aligned base and a leading dimension that is a multiple of the tile");
   static PerDeviceInt configured;  // per instantiation and per device
   configured.get([&] {
     PICARD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
@@ -42,20 +43,26 @@ static int launch_loss_i8_one(const PassLaunch& L, const uint8_t* xblob, uint8_t
   p.w = L.d_w; p.bias = nullptr; p.n_out = L.n_out; p.n_in = L.n_in; p.ldw = L.ldw;
   p.t_local = L.t_local; p.n_tiles = n_tiles; p.dp = make_dens_params(DENS, L.alpha);
   p.partial = L.d_partial; p.out = L.d_out; p.ld_out = L.ld_out;
-  i8::slice_w_kernel<<<1, 1024, 0, L.stream>>>(L.d_w, L.ldw, L.n_out, L.n_in, wblob);
+  i8::LossTail tail;
+  if (fin.counter != nullptr) {
+    *fin.counter_total += (unsigned int)grid;
+    tail.counter = fin.counter; tail.target = *fin.counter_total; tail.mom = L.d_mom; tail.finish = fin.finish; tail.which = fin.which;
+    if (fin.dims) tail.dims = *static_cast<const CoreDims*>(fin.dims);
+    tail.signs = fin.signs; tail.sc = static_cast<CoreScalars*>(fin.sc); tail.sc_map = static_cast<CoreScalars*>(fin.sc_map); tail.seq = fin.seq;
+  }
+  kern<<<(unsigned)grid, G::NTHREADS, G::SMEM_BYTES, L.stream>>>(xblob, p, tail, nullptr);
   PICARD_CUDA(cudaGetLastError());
-  kern<<<(unsigned)grid, G::NTHREADS, G::SMEM_BYTES, L.stream>>>(xblob, wblob, tmap_out, p, nullptr);
-  PICARD_CUDA(cudaGetLastError());
-  return 2 + rb_reduce(L, (int)grid, 1, 128, 128, false, false, true);
+  if (fin.counter != nullptr) return 1;
+  return 1 + rb_reduce(L, (int)grid, 1, 128, 128, false, false, true);
 }
 
-int launch_loss_i8(const PassLaunch& L, const uint8_t* xblob, uint8_t* wblob) {
+int launch_loss_i8(const PassLaunch& L, const uint8_t* xblob, const I8LossFinish& fin) {
   if (L.mode != PASS_LOSS || L.n_in > 128 || L.n_out > 128 || L.d_bias != nullptr)
     throw Error(PICARD_COMPUTATION_ERROR, "Computation error: the INT8 pass covers the LOSS mode for N <= 128 only");
   switch (L.dens) {
-    case DENS_TANH: return L.want_h ? launch_loss_i8_one<DENS_TANH, true>(L, xblob, wblob) : launch_loss_i8_one<DENS_TANH, false>(L, xblob, wblob);
-    case DENS_EXP: return L.want_h ? launch_loss_i8_one<DENS_EXP, true>(L, xblob, wblob) : launch_loss_i8_one<DENS_EXP, false>(L, xblob, wblob);
-    case DENS_CUBE: return L.want_h ? launch_loss_i8_one<DENS_CUBE, true>(L, xblob, wblob) : launch_loss_i8_one<DENS_CUBE, false>(L, xblob, wblob);
+    case DENS_TANH: return L.want_h ? launch_loss_i8_one<DENS_TANH, true>(L, xblob, fin) : launch_loss_i8_one<DENS_TANH, false>(L, xblob, fin);
+    case DENS_EXP: return L.want_h ? launch_loss_i8_one<DENS_EXP, true>(L, xblob, fin) : launch_loss_i8_one<DENS_EXP, false>(L, xblob, fin);
+    case DENS_CUBE: return L.want_h ? launch_loss_i8_one<DENS_CUBE, true>(L, xblob, fin) : launch_loss_i8_one<DENS_CUBE, false>(L, xblob, fin);
     default: break;
   }
   throw Error(PICARD_COMPUTATION_ERROR, "Computation error: bad density for the INT8 loss pass");

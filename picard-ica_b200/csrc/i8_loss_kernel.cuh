@@ -6,7 +6,8 @@
 // x1 is fixed for a whole fit, so it is sliced ONCE (slice_x_kernel) into tiles of NT samples, each tile already in the shared-
 // memory image the tensor core reads (K-major rows of 128 bytes = the 128 components of a sample, SWIZZLE_128B pattern), one
 // [NT x 128 B] block per digit, followed by the NT sample exponents: a tile is one contiguous bulk copy (cp.async.bulk, no
-// tensor map).  W' (128 x 128) is sliced per try by a one-CTA kernel (slice_w_kernel).
+// tensor map).  W' (128 x 128) is sliced by every CTA in its prologue; the partial row sums are combined, and on a single GPU the
+// loss of the try computed and published to the host, in the kernel's tail (LossTail): ONE launch per line-search try.
 //
 // loss_i8_kernel, one CTA per SM, 18 warps:
 //   warp 16 (one lane) : bulk copies of the x1 tiles into a 2-stage ring (mbarrier transaction bytes)
@@ -16,9 +17,8 @@
 //                        publishes the accumulators
 //   warps 0-15         : epilogue, thread = (row = TMEM lane, NT / 4 samples): tcgen05.ld of the 6 levels, accumulators returned
 //                        at once, exact 64-bit combination, scaling by exponent adds, log-likelihood, row sums per thread; Y'
-//                        through shared memory and ONE TMA store per warp and tile of its own [32 rows x NT / 4 samples] box
-//                        (no CTA-wide barrier: the warps only meet at the accumulator hand-over; the unit clips the ragged last
-//                        tile and the rows >= n_out); warps 0-3 first store W' into tensor memory
+//                        through a warp-private transpose in shared memory and coalesced 128-bit global stores (no CTA-wide
+//                        barrier: the warps only meet at the accumulator hand-over); warps 0-3 first store W' into tensor memory
 // tanh log-likelihood without a logarithm per element: sum_t [|y| + log(1 + e_t) / a] = sum |y| + log(prod (1 + e_t)) / a with
 // e_t = exp(-2 a |y_t|): the factors lie in [1, 2], so a thread keeps a running product, moves its exponent into an integer counter
 // once per tile and takes ONE logarithm at the end of the kernel (relative error of the product ~ sqrt(#factors) 2^-53).
@@ -27,14 +27,13 @@
 #pragma once
 #include "i8.cuh"
 #include "i8_common.cuh"
+#include "loss_point.cuh"
 
 namespace picard {
 namespace i8 {
 
 constexpr int KP = 128;                  // padded contraction length = bytes per operand row
-constexpr int SLICE_A_BYTES = 128 * KP;  // one digit of W': 128 rows x 128 bytes, plain row-major
-constexpr int W_EXP_OFFSET = S * SLICE_A_BYTES;
-static_assert(W_EXP_OFFSET + 128 * 4 == I8_WBLOB_BYTES, "wblob layout");
+constexpr int SLICE_A_BYTES = 128 * KP;  // one digit of W': 128 rows x 128 bytes
 
 template <int NT>
 struct LossGeom {
@@ -53,9 +52,8 @@ struct LossGeom {
   static constexpr int CPT = NT / 4;                               // samples per epilogue thread and tile
   static_assert(CPT % 4 == 0, "tcgen05.ld x4 / x8 granularity");
   static constexpr int NTHREADS = 32 * (NEW + 2);
-  static constexpr int YBOX_DOUBLES = 32 * CPT;                    // a warp's Y' box: [32 rows][CPT samples], dense
-  static constexpr int YBUFS = NT <= 32 ? 2 : 1;                   // boxes per warp (one is enough: the unit has read it long before the next tile)
-  static constexpr size_t SMEM_Y = (size_t)YBUFS * NEW * YBOX_DOUBLES * 8;
+  static_assert(CPT == 8 || CPT == 16, "the Y' transpose is written for 4 or 8 chunks per box row");
+  static constexpr size_t SMEM_Y = (size_t)NEW * 32 * CPT * 8;      // one [32 rows x CPT samples] transpose box per epilogue warp
   static constexpr size_t SMEM_B = (size_t)NSTAGE * STAGE_BYTES;
   static constexpr size_t SMEM_A = (size_t)(S - ATM) * SLICE_A_BYTES;
   static constexpr bool BIG = true;                                // the 2048-entry exp table (16 KB); the log table is not needed
@@ -63,6 +61,23 @@ struct LossGeom {
   static constexpr size_t SMEM_BYTES = SMEM_Y + SMEM_B + SMEM_A + TAB_BYTES + 8192 /* sums */ + 256;
   static_assert(SMEM_BYTES <= 232448, "shared memory");
   static constexpr uint32_t IDESC = make_idesc(NT);
+};
+
+// What follows the streaming part inside the kernel (instead of two more launches per line-search try): the per-CTA partial row sums
+// are combined in a fixed order by CTA 0 once every CTA has published its partial (device-wide counter), and -- on a single GPU,
+// where no exchange between ranks comes in between -- the loss of the try and its accept flag are computed and published to the
+// host (core.rs:39-85 after the sums, core.rs:127-132).
+struct LossTail {
+  unsigned int* counter = nullptr;   // device, monotonically increasing over launches; nullptr: no tail (partials only)
+  unsigned int target = 0;           // counter value once every CTA of THIS launch has arrived
+  double* mom = nullptr;             // reduced moments: the Sq and L sections are written
+  int finish = 0;                    // 1: also loss + accept flag + publish (single GPU)
+  int which = 0;                     // 0: a line-search try (new_loss, accept) ; 1: the current point (current_loss, loss_singular)
+  CoreDims dims{};
+  const double* signs = nullptr;
+  CoreScalars* sc = nullptr;
+  CoreScalars* sc_map = nullptr;
+  unsigned long long seq = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -141,34 +156,6 @@ __global__ void __launch_bounds__(8 * NT) slice_x_kernel(const double* __restric
   }
 }
 
-// slicing of W' (n_out x n_in, zero-padded to 128 x 128): one CTA, thread = (row, chunk); plain row-major digits (they go to
-// tensor memory row by row); the row exponents already carry COMBINE_EXP
-__global__ void __launch_bounds__(1024) slice_w_kernel(const double* __restrict__ w, int ldw, int n_out, int n_in, uint8_t* __restrict__ wblob) {
-  const int tid = threadIdx.x, r = tid >> 3, ch = tid & 7;
-  double v[16];
-  double m = 0.0;
-#pragma unroll
-  for (int kk = 0; kk < 16; ++kk) {
-    const int k = 16 * ch + kk;
-    v[kk] = (r < n_out && k < n_in) ? w[(size_t)r * ldw + k] : 0.0;
-    m = fmax(m, fabs(v[kk]));
-  }
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  const int e = bound_exponent(m);
-  uint64_t dg[16];
-#pragma unroll
-  for (int kk = 0; kk < 16; ++kk) dg[kk] = split_digits(v[kk], e);
-#pragma unroll
-  for (int p = 0; p < S; ++p) {
-    uint32_t q4[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) q4[kk >> 2] |= (uint32_t)((dg[kk] >> (8 * (S - 1 - p))) & 0xFF) << (8 * (kk & 3));
-    *reinterpret_cast<uint4*>(wblob + (size_t)p * SLICE_A_BYTES + r * KP + (ch << 4)) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
-  }
-  if (ch == 0) reinterpret_cast<int*>(wblob + W_EXP_OFFSET)[r] = e + COMBINE_EXP;
-}
-
 #ifndef I8_TRACE_SLOTS
 #define I8_TRACE_SLOTS 0
 #endif
@@ -178,8 +165,7 @@ __global__ void __launch_bounds__(1024) slice_w_kernel(const double* __restrict_
 // ---------------------------------------------------------------------------------------------------
 template <int DENS, bool WANT_SQ, int NT, int ABL = 0>
 __global__ void __launch_bounds__(LossGeom<NT>::NTHREADS, 1)  // 18 warps are allocated as 20: 96 registers per thread
-loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wblob, const __grid_constant__ CUtensorMap tmap_out,
-               const PassParams p, long long* __restrict__ trace) {
+loss_i8_kernel(const uint8_t* __restrict__ xblob, const PassParams p, const LossTail tail, long long* __restrict__ trace) {
   using G = LossGeom<NT>;
   constexpr int NEW = G::NEW, CPT = G::CPT, NSTAGE = G::NSTAGE;
   constexpr bool BIG = G::BIG;
@@ -202,7 +188,7 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
   constexpr bool NEED_TAB = !NO_DENS && (DENS == DENS_TANH || DENS == DENS_EXP);
   if (NEED_TAB) load_density_tables<BIG>(tab, false, tid, G::NTHREADS);
   if (tid == 0) {
-    ptx::mbar_init(a_full, 4);
+    ptx::mbar_init(a_full, NEW);
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1 + NEW); }
     ptx::mbar_init(acc_full, 1);
     ptx::mbar_init(acc_empty, NEW);
@@ -274,21 +260,40 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
     const int row = 32 * q4 + lane;
     double sl = 0.0, sq = 0.0, prod = 1.0;
     int pexp = 0;
-    if (cq == 0) {  // warps 0-3: this thread's row of every W' digit into tensor memory (4 K-steps of 32 bytes = 8 columns each)
+    // ---- W' (n_out x n_in f64, zero-padded to 128 x 128) -> balanced digits, in the kernel (no separate slicing launch per try):
+    // thread = (row, K-step cq = 32 of its 128 columns).  Row maximum across the four K-step warps through shared memory, then
+    // the digits of the thread's 32 values: one 32-byte K-step row per digit, into tensor memory (digits < ATM, tcgen05.st) or
+    // into the SWIZZLE_128B image in shared memory (the least significant digits).
+    int rexp;
+    {
+      const double* wrow = p.w + (size_t)row * p.ldw + 32 * cq;
+      double m = 0.0;
+#pragma unroll 4
+      for (int k = 0; k < 32; ++k) {
+        const double v = (row < p.n_out && 32 * cq + k < p.n_in) ? wrow[k] : 0.0;
+        m = fmax(m, fabs(v));
+      }
+      sums[cq * 128 + row] = m;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");
+      m = fmax(fmax(sums[row], sums[128 + row]), fmax(sums[256 + row], sums[384 + row]));
+      const int e = bound_exponent(m);
+      rexp = e + COMBINE_EXP;
 #pragma unroll 1
-      for (int pa = 0; pa < S; ++pa) {
-        const uint4* src = reinterpret_cast<const uint4*>(wblob + (size_t)pa * SLICE_A_BYTES + (size_t)row * KP);
-        if (pa < G::ATM) {
+      for (int half = 0; half < 2; ++half) {
+        uint64_t dg[16];
 #pragma unroll
-          for (int k = 0; k < KP / 32; ++k) {
-            const uint4 u0 = src[2 * k], u1 = src[2 * k + 1];
-            const uint32_t v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-            tmem_st8(tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(G::TMEM_A + 8 * (4 * pa + k)), v);
-          }
-        } else {  // the least significant digits: shared memory, 16-byte chunk c of row r at position c ^ (r & 7)
+        for (int k = 0; k < 16; ++k) {
+          const int col = 32 * cq + 16 * half + k;
+          dg[k] = split_digits((row < p.n_out && col < p.n_in) ? wrow[16 * half + k] : 0.0, e);
+        }
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8)
-            *reinterpret_cast<uint4*>(sa + (size_t)(pa - G::ATM) * SLICE_A_BYTES + row * KP + ((c8 ^ (row & 7)) << 4)) = src[c8];
+        for (int pa = 0; pa < S; ++pa) {
+          uint32_t w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int k = 0; k < 16; ++k) w4[k >> 2] |= (uint32_t)((dg[k] >> (8 * (S - 1 - pa))) & 0xFF) << (8 * (k & 3));
+          if (pa < G::ATM) tmem_st4(tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(G::TMEM_A + 8 * (4 * pa + cq) + 4 * half), w4);
+          else *reinterpret_cast<uint4*>(sa + (size_t)(pa - G::ATM) * SLICE_A_BYTES + row * KP + (((2 * cq + half) ^ (row & 7)) << 4)) =
+                   make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
       }
       tmem_wait_st();
@@ -296,8 +301,8 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");  // `sums` is reused for the row sums at the end
     }
-    const int rexp = reinterpret_cast<const int*>(wblob + W_EXP_OFFSET)[row];  // row exponent + COMBINE_EXP
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int st = (int)(it % NSTAGE);
       const int64_t t0 = (tile0 + it * tstride) * NT + CPT * cq;
@@ -329,10 +334,15 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty);
         }
+        // = combine_levels(): hi + 2^-24 lo, rounded once -- without the two 64-bit integer-to-double conversions per element (XU
+        // pipe, 8 cycles per warp instruction): for |v| < 2^51 the bit pattern of M + v (M = 1.5 2^52) is M's pattern plus v, so
+        //   hi + 2^-24 lo = fma(M + lo, 2^-24, (M + hi) - M (1 + 2^-24)),  every intermediate exact, one rounding at the end
 #pragma unroll
-        for (int e = 0; e < CPT; ++e) {  // = combine_levels(): hi + 2^-24 lo, rounded once
+        for (int e = 0; e < CPT; ++e) {
           const long long v = (long long)c[0][e] * 65536 + (long long)c[1][e] * 256 + (long long)c[2][e];
-          if (grp == 0) y[e] = (double)v; else y[e] = fma((double)v, 5.9604644775390625e-08 /* 2^-24 */, y[e]);
+          const double raw = __longlong_as_double(v + 0x4338000000000000LL);  // M + v
+          if (grp == 0) y[e] = raw - 6755399441055744.0 * (1.0 + 5.9604644775390625e-08);
+          else y[e] = fma(raw, 5.9604644775390625e-08 /* 2^-24 */, y[e]);
         }
       }
       if (tr) trace[it * 8 + 6] = clock64();
@@ -376,28 +386,33 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
 #pragma unroll
         for (int e = 0; e < CPT; ++e) sl += y[e];
       }
-      // Y' leaves through shared memory and the TMA unit (a thread's samples are CPT * 8 bytes of ITS row: direct stores would be
-      // 32 different lines per instruction).  One box per warp: [32 rows x CPT samples], dense rows; two buffers, the store of
-      // tile it - 2 has been read by the unit before the buffer is written again (wait_group.read 1 by the issuing lane).
+      // Y' leaves through a warp-private transpose in shared memory and COALESCED 128-bit global stores: a thread owns CPT contiguous
+      // samples of its row (direct stores would touch 32 lines per instruction), so the warp writes its [32 rows x CPT samples] box
+      // (16-byte chunk c of row r at position c ^ swz(r): conflict-free), re-reads it chunk-major and stores 512 contiguous-by-row
+      // bytes per instruction.  Only __syncwarp(): no proxy fence, no TMA store, no CTA-wide barrier on the critical path (the TMA
+      // store path spent ~9 % of the epilogue's time in fence.proxy.async: profiles/summary_r02*.txt).  The Y store's leading
+      // dimension is a multiple of 64 samples, so whole tiles are in bounds; columns >= t_local receive the zero padding of x1.
       if (!NO_STORE && p.out != nullptr) {
-        double* yb = ysm + (size_t)(G::YBUFS * warp + (G::YBUFS == 2 ? (int)(it & 1) : 0)) * G::YBOX_DOUBLES;
-        if (lane == 0) {
-          if (G::YBUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-        __syncwarp();
+        constexpr int CH = CPT / 2;              // 16-byte chunks per box row (8 or 4)
+        constexpr int RPI = 32 / CH;             // rows per store instruction
+        unsigned char* yb = reinterpret_cast<unsigned char*>(ysm) + (size_t)warp * (32 * CPT * 8);
+        __syncwarp();                            // the previous tile's reads of the box are done
 #pragma unroll
-        for (int e = 0; e < CPT; e += 2) *reinterpret_cast<double2*>(yb + lane * CPT + e) = make_double2(y[e], y[e + 1]);
-        ptx::fence_proxy_async();
+        for (int c2 = 0; c2 < CH; ++c2)
+          *reinterpret_cast<double2*>(yb + lane * (CPT * 8) + ((c2 ^ ((CH == 8 ? lane : (lane >> 1)) & (CH - 1))) << 4)) = make_double2(y[2 * c2], y[2 * c2 + 1]);
         __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmap_out, yb, (int)((tile0 + it * tstride) * NT + CPT * cq), 32 * q4);
-          bulk_commit();
+        const int c2 = lane & (CH - 1);
+        const int64_t tcol = (tile0 + it * tstride) * NT + CPT * cq + 2 * c2;
+#pragma unroll
+        for (int i = 0; i < 32 / RPI; ++i) {
+          const int rr = (lane / CH) + RPI * i;  // row of the box
+          const double2 v = *reinterpret_cast<const double2*>(yb + rr * (CPT * 8) + ((c2 ^ ((CH == 8 ? rr : (rr >> 1)) & (CH - 1))) << 4));
+          const int grow = 32 * q4 + rr;
+          if (grow < p.n_out) *reinterpret_cast<double2*>(p.out + (size_t)grow * p.ld_out + tcol) = v;
         }
       }
       if (tr) trace[it * 8 + 7] = clock64();
     }
-    if (!NO_STORE && p.out != nullptr && lane == 0) bulk_wait0();
     if (DENS == DENS_TANH && !NO_DENS) sl = fma(fma((double)pexp, 6.931471805599453094e-01, log(prod)), p.dp.inv_alpha, sl);
     // the column quarters of a row live in warps q4, q4 + 4, q4 + 8, q4 + 12
     if (cq > 0) { sums[(cq - 1) * 256 + row] = sl; sums[(cq - 1) * 256 + 128 + row] = sq; }
@@ -408,9 +423,51 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const uint8_t* __restrict__ wb
       out[row] = 0.0; out[128 + row] = sq; out[256 + row] = sl;
     }
   }
+  __threadfence();  // the partial (written by the cq == 0 threads above) is visible device-wide before this CTA is counted
   tc_fence_before();
   __syncthreads();
   if (warp == NEW + 1) tmem_dealloc512(tmem);
+  if (tail.counter != nullptr) {
+    if (blockIdx.x != 0) {
+      if (tid == 0) atomicAdd(tail.counter, 1u);
+    } else {
+      if (tid == 0) {
+        atomicAdd(tail.counter, 1u);
+        while ((int)(*reinterpret_cast<volatile unsigned int*>(tail.counter) - tail.target) < 0) __nanosleep(64);
+        __threadfence();
+      }
+      __syncthreads();
+      // fixed-order sum of the per-CTA partials [Sd (unused) | Sq | L]: eight independent chains per element (latency-bound)
+      if (tid < 256) {
+        const int r = tid & 127, sec = tid >> 7;
+        const double* pp = p.partial + 128 + sec * 128 + r;
+        double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int b = 0;
+        for (; b + 8 <= (int)gridDim.x; b += 8) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] += __ldcg(pp + (size_t)(b + u) * 384);
+        }
+        for (int u = 0; b < (int)gridDim.x; ++b, ++u) acc[u] += __ldcg(pp + (size_t)b * 384);
+        if (r < p.n_out)
+          tail.mom[(sec == 0 ? mom_off_sq(p.n_out) : mom_off_ll(p.n_out)) + r] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+      }
+      __syncthreads();
+      if (tail.finish && warp == 0) {
+        bool sing;
+        const double l = small::loss_of_point_warp(tail.dims, tail.mom, tail.signs, &sing);
+        if (lane == 0) {
+          if (tail.which == 0) {
+            tail.sc->new_loss = l;
+            tail.sc->accept = (l < tail.sc->current_loss) ? 1 : 0;
+          } else {
+            tail.sc->current_loss = l;
+            tail.sc->loss_singular = sing ? 1 : 0;
+          }
+          publish_scalars(tail.sc, tail.sc_map, tail.seq);
+        }
+      }
+    }
+  }
 }
 
 }  // namespace i8

@@ -1,5 +1,6 @@
 // N x N device kernels of the core loop.  See small.cuh.  Reference citations per kernel.
 #include "small.cuh"
+#include "loss_point.cuh"
 
 #include <cmath>
 
@@ -267,34 +268,14 @@ __global__ void __launch_bounds__(BT1) front_kernel(FrontArgs a) {
     dm = fmax(dm, fabs(v));
   }
   const double nd = block_max(dm, sh);
-  if (tid == 0) a.sc->norm_d = nd;
+  if (tid == 0) {
+    a.sc->norm_d = nd;
+    publish_scalars(a.sc, a.sc_map, a.seq);
+  }
 }
 
-// one warp: lane-strided partial sums + shuffle tree (fixed order, deterministic)
-__device__ double loss_of_point_warp(const CoreDims& d, const double* mom, const double* signs, bool* singular) {
-  const int n = d.n, lane = threadIdx.x & 31;
-  const double tf = d.t_total;
-  *singular = false;
-  double base = 0.0;
-  if (!d.ortho) {
-    const double* ex = mom + mom_size(n);
-    if (ex[1] == 0.0) { *singular = true; return 1e15; }
-    base = -ex[0];
-  }
-  const double* L = mom + mom_off_ll(n);
-  const double* Sq = mom + mom_off_sq(n);
-  double part = 0.0;
-  for (int i = lane; i < n; i += 32) {
-    const double s = signs ? signs[i] : 1.0;
-    part += s * L[i] / tf;
-    if (d.extended && !d.ortho) part += 0.5 * Sq[i] / tf;
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  return base + part;
-}
-
-__global__ void loss_kernel(CoreDims d, const double* mom, const double* signs, CoreScalars* sc, int which) {
+__global__ void loss_kernel(CoreDims d, const double* mom, const double* signs, CoreScalars* sc, int which, CoreScalars* sc_map,
+                            unsigned long long seq) {
   bool sing;
   const double l = loss_of_point_warp(d, mom, signs, &sing);
   if (threadIdx.x != 0) return;
@@ -305,6 +286,7 @@ __global__ void loss_kernel(CoreDims d, const double* mom, const double* signs, 
     sc->current_loss = l;
     sc->loss_singular = sing ? 1 : 0;
   }
+  publish_scalars(sc, sc_map, seq);
 }
 
 __global__ void accept_kernel(const double* D, double alpha, double* S_prev, int64_t count, CoreScalars* sc) {
@@ -998,8 +980,9 @@ int iteration_front(const FrontArgs& a, cudaStream_t st) {
   LAUNCH_CHECK();
   return 1;
 }
-int loss_from_moments(const CoreDims& d, const double* mom, const double* signs, CoreScalars* sc, int which, cudaStream_t st) {
-  loss_kernel<<<1, 32, 0, st>>>(d, mom, signs, sc, which);
+int loss_from_moments(const CoreDims& d, const double* mom, const double* signs, CoreScalars* sc, int which, cudaStream_t st,
+                      CoreScalars* sc_map, unsigned long long seq) {
+  loss_kernel<<<1, 32, 0, st>>>(d, mom, signs, sc, which, sc_map, seq);
   LAUNCH_CHECK();
   return 1;
 }

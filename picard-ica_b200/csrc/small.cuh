@@ -20,7 +20,24 @@ struct CoreScalars {
   int32_t have_g_old, have_prev_step;
   int32_t loss_singular;  // the initial / recomputed loss hit a singular W (core.rs:188-190, 321-325)
   int32_t pad;
+  unsigned long long seq; // host mirror only: written LAST by the publishing kernel (see publish_scalars)
 };
+
+#ifdef __CUDACC__
+// The host decides after every line-search try and every iteration front.  Instead of a D2H copy + stream synchronisation
+// (~15 us of latency each) the kernel that finalises the scalars writes them into the host's pinned mirror (mapped into the
+// device address space) and then, after a system-scope fence, a sequence number the host is spinning on.
+__device__ __forceinline__ void publish_scalars(const CoreScalars* sc, CoreScalars* map, unsigned long long seq) {
+  if (map == nullptr) return;
+  const volatile CoreScalars* s = sc;
+  map->gradient_norm = s->gradient_norm; map->current_loss = s->current_loss; map->new_loss = s->new_loss; map->norm_d = s->norm_d;
+  map->last_r = s->last_r; map->sign_change = s->sign_change; map->accept = s->accept; map->mem_len = s->mem_len;
+  map->mem_head = s->mem_head; map->have_g_old = s->have_g_old; map->have_prev_step = s->have_prev_step;
+  map->loss_singular = s->loss_singular;
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long*>(&map->seq) = seq;
+}
+#endif
 
 // Per-point extras appended to a moment buffer: [logdet, detsign] at offset mom_size(n).
 constexpr int MOM_EXTRA = 2;
@@ -54,6 +71,8 @@ struct FrontArgs {
   double* mem_s; double* mem_y; double* mem_r;  // ring buffers [m][n*n], [m]
   double* q; double* D;    // work / output direction
   CoreScalars* sc;
+  CoreScalars* sc_map = nullptr;   // host mirror to publish to (nullptr: none)
+  unsigned long long seq = 0;
   int first_iter;
   int do_lbfgs;            // 1: full; 0: front only (test hook); 2: direction only from G/H/hoff/memory in place (test hook)
 };
@@ -61,7 +80,8 @@ int iteration_front(const FrontArgs& a, cudaStream_t st);
 
 // Loss of a point from its moments (core.rs:39-85 after the sums): writes sc->new_loss and sc->accept
 // (which = 0) or sc->current_loss (which = 1; singular -> 1e15 and sc->loss_singular).
-int loss_from_moments(const CoreDims& d, const double* mom, const double* signs, CoreScalars* sc, int which, cudaStream_t st);
+int loss_from_moments(const CoreDims& d, const double* mom, const double* signs, CoreScalars* sc, int which, cudaStream_t st,
+                      CoreScalars* sc_map = nullptr, unsigned long long seq = 0);
 
 // After an accepted (or forced) try: S_prev = alpha * D, current_loss = new_loss, have_prev_step = 1;
 // extended with covariance = I: C = W W^T (core.rs:375-379).

@@ -98,16 +98,15 @@ static void print_trace(const char* what, const std::vector<long long>& tr, cons
 }
 
 template <int ABL>
-static void run_loss(const uint8_t* xblob, const uint8_t* wblob, double* yout, int64_t ld, int64_t t, int n, double* partial, int sms, int reps,
+static void run_loss(const uint8_t* xblob, const double* w, double* yout, int64_t ld, int64_t t, int n, double* partial, int sms, int reps,
                      long long* d_trace) {
   using G = i8::LossGeom<I8_TILE>;
   auto kern = i8::loss_i8_kernel<DENS_TANH, false, I8_TILE, ABL>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
-  const CUtensorMap tm = make_tmap_box(yout, ld, t, n, G::CPT, 32, false);
   PassParams p{};
-  p.n_out = n; p.n_in = n; p.t_local = t; p.n_tiles = (t + I8_TILE - 1) / I8_TILE; p.dp = make_dens_params(DENS_TANH, 1.0); p.partial = partial; p.out = yout; p.ld_out = ld;
+  p.w = w; p.ldw = n; p.n_out = n; p.n_in = n; p.t_local = t; p.n_tiles = (t + I8_TILE - 1) / I8_TILE; p.dp = make_dens_params(DENS_TANH, 1.0); p.partial = partial; p.out = yout; p.ld_out = ld;
   const int grid = sms;
-  float ms = time_ms([&] { kern<<<grid, G::NTHREADS, G::SMEM_BYTES>>>(xblob, wblob, tm, p, d_trace); }, reps);
+  float ms = time_ms([&] { kern<<<grid, G::NTHREADS, G::SMEM_BYTES>>>(xblob, p, i8::LossTail{}, d_trace); }, reps);
   CK(cudaGetLastError());
   printf("{\"kernel\": \"loss_i8\", \"ablation\": %d, \"T\": %lld, \"ms\": %.4f, \"ms_at_1e7\": %.3f}\n", ABL, (long long)t, ms, ms * 1e7 / (double)t);
   if (ABL & 4) {
@@ -128,7 +127,7 @@ static float run_grad(const double* y, int64_t ld, int64_t t, int n, const int* 
   const CUtensorMap tm = make_tmap(y, ld, t, n, 128);
   i8::GradParams p{};
   p.n = n; p.t_local = t; p.n_tiles = (t + 31) / 32; p.dp = make_dens_params(DENS_TANH, 1.0); p.rowexp = rowexp; p.psi_exp = i8::psi_exponent(DENS_TANH, 1.0);
-  p.partial = partial;
+  p.partial = partial; p.counter = nullptr; p.target = 0; p.mom = nullptr;
   int64_t n_tg = sms / 2; if (n_tg > p.n_tiles) n_tg = p.n_tiles;
   float ms = time_ms([&] { kern<<<(unsigned)(2 * n_tg), G::NTHREADS, G::SMEM_BYTES>>>(tm, p, d_trace); }, reps);
   CK(cudaGetLastError());
@@ -169,9 +168,9 @@ int main(int argc, char** argv) {
   int dev = 0, sms = 0;
   CK(cudaSetDevice(dev));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t ld = (T + 15) / 16 * 16;
+  const int64_t ld = (T + 63) / 64 * 64;
   double *x, *y, *w, *partial, *xstats, *ynaive, *gnaive, *sdnaive;
-  uint8_t *xblob, *wblob;
+  uint8_t* xblob;
   int* rowexp;
   long long* d_trace;
   CK(cudaMalloc(&x, sizeof(double) * n * ld)); CK(cudaMalloc(&y, sizeof(double) * n * ld));
@@ -179,7 +178,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&w, sizeof(double) * n * n));
   CK(cudaMalloc(&partial, sizeof(double) * sms * 2 * (2 * 128 * 128 + 3 * 128)));
   CK(cudaMalloc(&xstats, sizeof(double) * I8_XSTATS));
-  CK(cudaMalloc(&xblob, (size_t)((T + I8_TILE - 1) / I8_TILE) * i8::LossGeom<I8_TILE>::TILE_BYTES + 1024)); CK(cudaMalloc(&wblob, I8_WBLOB_BYTES));
+  CK(cudaMalloc(&xblob, (size_t)((T + I8_TILE - 1) / I8_TILE) * i8::LossGeom<I8_TILE>::TILE_BYTES + 1024));
   CK(cudaMalloc(&rowexp, 128 * sizeof(int)));
   CK(cudaMalloc(&d_trace, I8_TRACE_SLOTS * 8 * sizeof(long long))); CK(cudaMemset(d_trace, 0, I8_TRACE_SLOTS * 8 * sizeof(long long)));
   fill_kernel<<<sms * 8, 256>>>(x, n, T, ld, 1234, 1.0);
@@ -194,7 +193,6 @@ int main(int argc, char** argv) {
     i8::slice_x_kernel<I8_TILE><<<(unsigned)std::min<int64_t>(n_tiles, sms * 8), 8 * I8_TILE>>>(x, ld, T, n, n_tiles, xblob, xstats);
   }, 1);
   CK(cudaGetLastError());
-  i8::slice_w_kernel<<<1, 1024>>>(w, n, n, n, wblob);
   CK(cudaDeviceSynchronize());
   std::vector<double> hs(I8_XSTATS);
   CK(cudaMemcpy(hs.data(), xstats, sizeof(double) * I8_XSTATS, cudaMemcpyDeviceToHost));
@@ -203,7 +201,7 @@ int main(int argc, char** argv) {
   printf("{\"kernel\": \"slice_x\", \"ms\": %.3f, \"mean_bound\": %.3f, \"min_row_rms\": %.4f, \"max_norm\": %.3f}\n", ms_slice, hs[0] / T, sqrt(min_ms), sqrt(mx2));
 
   if (only) {
-    run_loss<0>(xblob, wblob, y, ld, T, n, partial, sms, 1, d_trace);
+    run_loss<0>(xblob, w, y, ld, T, n, partial, sms, 1, d_trace);
     i8::row_exponent_kernel<<<16, 256>>>(w, n, xstats, rowexp);
     CK(cudaDeviceSynchronize());
     run_grad<0, 0>(y, ld, T, n, rowexp, partial, sms, 1, d_trace);
@@ -211,7 +209,7 @@ int main(int argc, char** argv) {
     return 0;
   }
   // ---- LOSS kernel: timing, ablations, trace
-  run_loss<0>(xblob, wblob, y, ld, T, n, partial, sms, reps, d_trace);
+  run_loss<0>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);
   // correctness of the stored Y' on the first 8192 samples
   {
     const int64_t tc = std::min<int64_t>(T, 8192);
@@ -224,11 +222,11 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < a.size(); ++i) { num = fmax(num, fabs(a[i] - b[i])); den = fmax(den, fabs(a[i])); }
     printf("{\"check\": \"loss_i8 Y' vs naive f64\", \"max_abs_err\": %.3e, \"max_abs_y\": %.3f, \"rel\": %.3e}\n", num, den, num / den);
   }
-  run_loss<1>(xblob, wblob, y, ld, T, n, partial, sms, reps, d_trace);
-  run_loss<2>(xblob, wblob, y, ld, T, n, partial, sms, reps, d_trace);
-  run_loss<3>(xblob, wblob, y, ld, T, n, partial, sms, reps, d_trace);
-  run_loss<4>(xblob, wblob, y, ld, T, n, partial, sms, 1, d_trace);
-  run_loss<0>(xblob, wblob, y, ld, T, n, partial, sms, reps, d_trace);  // leaves the full Y' for the gradient kernel
+  run_loss<1>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);
+  run_loss<2>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);
+  run_loss<3>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);
+  run_loss<4>(xblob, w, y, ld, T, n, partial, sms, 1, d_trace);
+  run_loss<0>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);  // leaves the full Y' for the gradient kernel
 
   // ---- gradient kernel: correctness of both layouts on a short prefix, then timing
   i8::row_exponent_kernel<<<16, 256>>>(w, n, xstats, rowexp);

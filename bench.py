@@ -464,7 +464,8 @@ def _main(out):
                               jade_it=wl.get("jade_it"), comm=comm, device=local_rank)
         os.environ.setdefault("PICARD_TRACE", "1")  # stage timings of every e2e call on stderr (a few extra stream syncs)
         runs = []
-        for _rep in range(3):  # three complete calls; the median is reported, all three are listed
+        first_call_s = None
+        for _rep in range(4):  # one untimed warm-up call, then three complete timed calls; the median is reported, all are listed
             res = None
             barrier()
             e_t0 = time.perf_counter()
@@ -476,15 +477,20 @@ def _main(out):
             te = torch.tensor([e_s], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            if _rep == 0:  # the process's first fit also page-locks the arena the `sources` result lives in (seconds, once per process)
+                first_call_s = float(te[0])
+                continue
             runs.append((float(te[0]), res.stats, res.n_iterations, bool(res.converged), gn))
         runs.sort(key=lambda r: r[0])
         e_s, st_e, n_it_e, conv_e, gn = runs[1]
         e2e = {"value": n_it_e / e_s, "unit": UNIT, "h2d_bytes_per_step": st_e["h2d_bytes"] / max(n_it_e, 1),
                "d2h_bytes_per_step": st_e["d2h_bytes"] / max(n_it_e, 1), "iterations": n_it_e,
                "converged": conv_e, "gradient_norm": gn, "seconds": e_s, "seconds_all_runs": [r[0] for r in runs],
+               "warmup_calls": 1, "first_call_seconds": first_call_s,
                "core_ms": st_e["core_ms"], "preprocess_ms": st_e["preprocess_ms"], "h2d_ms": st_e["h2d_ms"], "d2h_ms": st_e["d2h_ms"],
                "what": "Picard.fit_with_config on pinned host X (this rank's shard): H2D, centering, whitening, fit to convergence, "
-                       "D2H of sources; iterations / wall seconds (median of 3 calls)"}
+                       "D2H of sources into the library's pinned result arena; iterations / wall seconds (median of 3 calls after one warm-up "
+                       "call that also page-locks the arena: first_call_seconds)"}
         del res, runs
 
     cpu = None

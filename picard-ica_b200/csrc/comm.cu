@@ -2,6 +2,7 @@
 // NCCL is loaded lazily with dlopen so single-GPU users carry no NCCL dependency; inside a Python process
 // that already imported torch this resolves to torch's bundled libnccl.so.2, otherwise to the system one.
 #include "engine.cuh"
+#include "p2p.cuh"
 
 #include <dlfcn.h>
 
@@ -72,21 +73,12 @@ void comm_unique_id(char id[PICARD_UNIQUE_ID_BYTES]) {
 
 }  // namespace picard
 
-// Peer "mailbox" of the one-shot allreduce (see p2p_allreduce_kernel): every rank owns [2 parities][nranks slots][P2P_MAX doubles]
-// plus arrival counters, and maps every peer's mailbox through CUDA IPC (NVLink / NVSwitch peer access).
-constexpr int P2P_MAX_RANKS = 8;
-constexpr size_t P2P_MAX_DOUBLES = 2 * 128 * 128 + 3 * 128 + 8;  // the largest packed moment buffer the core loop exchanges (N <= 128)
-constexpr int P2P_PARTS = 4;                                      // CTAs per destination rank
-struct P2PPeers {
-  double* box[P2P_MAX_RANKS];        // box[q]: rank q's mailbox as seen from this rank (box[rank] = the local allocation)
-  unsigned int* flags[P2P_MAX_RANKS];
-};
 struct picard_comm {
   void* nccl = nullptr;
   int rank = 0, nranks = 1, device = 0;
   bool p2p = false;
   void* p2p_local = nullptr;         // this rank's mailbox allocation (flags first, then the slots)
-  P2PPeers peers{};
+  picard::P2PPeers peers{};
   unsigned long long p2p_calls = 0;  // allreduces issued so far (parity = calls & 1)
 };
 
@@ -95,7 +87,6 @@ namespace picard {
 namespace {
 constexpr size_t P2P_FLAG_BYTES = 4096;  // [2][P2P_MAX_RANKS] counters, padded
 constexpr size_t P2P_BOX_BYTES = P2P_FLAG_BYTES + sizeof(double) * 2 * P2P_MAX_RANKS * P2P_MAX_DOUBLES;
-__host__ __device__ inline size_t p2p_slot(int parity, int src, int nranks) { return ((size_t)parity * P2P_MAX_RANKS + src) * P2P_MAX_DOUBLES; }
 
 // One-shot allreduce (sum, f64) of a small buffer over NVLink peer memory, ONE launch per call, bit-identical on every rank:
 //   push : CTA (dst, part) copies part `part` of the local buffer into rank dst's mailbox slot [parity][this rank] (16-byte peer
@@ -112,7 +103,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(double* __restrict__
   const int per = (n2 + P2P_PARTS - 1) / P2P_PARTS;
   const int lo = part * per, hi = lo + per < n2 ? lo + per : n2;
   {
-    double2* out = reinterpret_cast<double2*>(peers.box[dst] + p2p_slot(parity, rank, nranks));
+    double2* out = reinterpret_cast<double2*>(peers.box[dst] + p2p_slot(parity, rank));
     const double2* in = reinterpret_cast<const double2*>(buf);
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) out[i] = in[i];
     __threadfence_system();
@@ -129,7 +120,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(double* __restrict__
   // this CTA's slice of the result: gridDim.x slices of double2 units
   const int nsl = gridDim.x, sper = (n2 + nsl - 1) / nsl;
   const int slo = blockIdx.x * sper, shi = slo + sper < n2 ? slo + sper : n2;
-  const double2* box = reinterpret_cast<const double2*>(peers.box[rank] + p2p_slot(parity, 0, nranks));
+  const double2* box = reinterpret_cast<const double2*>(peers.box[rank] + p2p_slot(parity, 0));
   const size_t stride2 = P2P_MAX_DOUBLES / 2;
   for (int i = slo + threadIdx.x; i < shi; i += blockDim.x) {
     double2 acc = __ldcv(box + i);
@@ -249,6 +240,16 @@ void comm_allreduce_sum(picard_comm* c, double* d_buf, size_t count, cudaStream_
   }
   nccl_check(api().all_reduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, c->nccl, st), "ncclAllReduce");
 }
+// For kernels that carry the exchange in their own tail: the next call's parity / expected counter value (advances the call count).
+bool comm_p2p_next(picard_comm* c, size_t count, P2PCall* out) {
+  if (!c || c->nranks == 1 || !c->p2p || count > P2P_MAX_DOUBLES - 2) return false;
+  out->peers = c->peers; out->rank = c->rank; out->nranks = c->nranks;
+  out->parity = (int)(c->p2p_calls & 1);
+  out->expect = (unsigned int)((c->p2p_calls / 2 + 1) * P2P_PARTS);
+  ++c->p2p_calls;
+  return true;
+}
+
 void comm_allreduce_sum2(picard_comm* c, double* a, size_t na, double* b, size_t nb, cudaStream_t st) {
   if (!c || c->nranks == 1) return;
   if (c->p2p) {  // two one-shot exchanges (each one launch)

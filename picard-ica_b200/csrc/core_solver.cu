@@ -13,6 +13,7 @@
 //     (core.rs:317-329) and the initial loss (core.rs:185) need no extra pass.
 #include "engine.cuh"
 #include "i8.cuh"
+#include "p2p.cuh"
 
 #include <chrono>
 #include <map>
@@ -200,8 +201,8 @@ bool CoreSolver::i8_prepare() {
   if (!forced && !cov_identity_) return false;
   try {
     xs8_.alloc(i8_blob_bytes(t_local_));
-    i8_counter_.alloc(2);
-    PICARD_CUDA(cudaMemsetAsync(i8_counter_.p, 0, 2 * sizeof(unsigned int), st_));
+    i8_counter_.alloc(3);
+    PICARD_CUDA(cudaMemsetAsync(i8_counter_.p, 0, 3 * sizeof(unsigned int), st_));
     xstats_.alloc((size_t)I8_XSTATS);
     rowexp_.alloc(128);
   } catch (const Error&) {  // no memory for the digit image: the FP64 kernels need none
@@ -246,25 +247,32 @@ bool CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
   else stats_.loss_passes++;
   resolve_pass_time();
   PICARD_CUDA(cudaEventRecord(ev_a_, st_));
-  bool finished = false;
+  bool finished = false, exchanged = false;
+  const bool single = !(comm_ && comm_size(comm_) > 1);
+  P2PCall px;
   if (use_i8) {
-    // one launch: W' digits, streaming, deterministic reduction of the partials [, on a single GPU: loss + accept flag + publish]
-    const bool single = !(comm_ && comm_size(comm_) > 1);
+    // one launch: W' digits, streaming, deterministic reduction of the partials, [exchange between the ranks over peer memory,]
+    // loss + accept flag + publish -- on any number of GPUs when the peer mailboxes are available
     I8LossFinish fin;
     fin.counter = i8_counter_.p; fin.counter_total = &i8_counter_total_[0];
-    if (finish_which >= 0 && single) {
+    if (!single && comm_p2p_next(comm_, 2 * (size_t)dims_.n, &px)) { fin.px = &px; exchanged = true; }
+    if (finish_which >= 0 && (single || exchanged)) {
       fin.finish = 1; fin.which = finish_which; fin.dims = &dims_; fin.signs = finish_signs; fin.sc = sc_dev_.p; fin.sc_map = sc_host_.p;
       fin.seq = next_seq();
       finished = true;
     }
     stats_.kernel_launches += launch_loss_i8(L, xs8_.p, fin);
     stats_.i8_loss_passes++;
+  } else if (use_i8_grad) {
+    const size_t nn = (size_t)dims_.n * dims_.n;
+    if (!single && 2 * (L.sm_count / 2) <= L.sm_count && comm_p2p_next(comm_, nn + (size_t)dims_.n, &px)) exchanged = true;
+    stats_.kernel_launches += launch_grad_i8(L, rowexp_.p, i8_counter_.p + 1, &i8_counter_total_[1], exchanged ? &px : nullptr);
+    stats_.i8_grad_passes++;
   }
-  else if (use_i8_grad) { stats_.kernel_launches += launch_grad_i8(L, rowexp_.p, i8_counter_.p + 1, &i8_counter_total_[1]); stats_.i8_grad_passes++; }
   else stats_.kernel_launches += launch_pass(L);
   PICARD_CUDA(cudaEventRecord(ev_b_, st_));
-  // one NCCL allreduce of exactly what this pass produced
-  if (comm_ && comm_size(comm_) > 1) {
+  // one allreduce of exactly what this pass produced -- unless the pass kernel has carried the exchange itself
+  if (comm_ && comm_size(comm_) > 1 && !exchanged) {
     const int n = dims_.n;
     const size_t nn = (size_t)n * n;
     if (mode == PASS_LOSS) comm_allreduce_sum(comm_, d_mom + mom_off_sq(n), 2 * (size_t)n, st_);
@@ -333,7 +341,9 @@ void CoreSolver::try_point(double alpha, bool speculate, int try_index, int trie
   if (dims_.ortho) {  // W' = expm(alpha D) W (core.rs:119,125)
     if (try_index == 0) {  // every candidate alpha / 2^t of this search from one Taylor run (bit-identical to one run per try)
       if (!wt_all_.p) wt_all_.alloc((size_t)small::EXPM_NC * n * n);
-      const int r = small::matrix_exp_candidates(D_, alpha, sc_host_.p->norm_d, n, tries_planned, ew_, W_, wt_all_.p, st_);
+      // the first candidates only: 95 % of the line searches end within four tries (2.4 on average at c3), and every candidate costs
+      // one more N x N x N product in the kernel; later tries take the per-try kernel (same bits)
+      const int r = small::matrix_exp_candidates(D_, alpha, sc_host_.p->norm_d, n, tries_planned < 4 ? tries_planned : 4, ew_, W_, wt_all_.p, st_);
       cand_ready_ = r > 0 ? r : 0;
       if (r > 0) stats_.kernel_launches += 1;
     }

@@ -22,6 +22,9 @@ int comm_rank(const picard_comm* c);
 int comm_size(const picard_comm* c);
 void comm_allreduce_sum(picard_comm* c, double* d_buf, size_t count, cudaStream_t st);
 void comm_allreduce_sum2(picard_comm* c, double* a, size_t na, double* b, size_t nb, cudaStream_t st);
+struct P2PCall;
+// peer-memory exchange carried by a pass kernel's own tail: false = not available (single rank, no peer access, payload too large)
+bool comm_p2p_next(picard_comm* c, size_t count, P2PCall* out);
 
 // PICARD_TRACE diagnostics: report driver allocator calls that take more than 5 ms
 double trace_now_ms();
@@ -149,8 +152,8 @@ class CoreSolver {
   int64_t ldy_ = 0;        // leading dimension of ybuf_
   // INT8 tensor-core passes (i8_loss.cu, i8_grad.cu): decided once per solver at the first LOSS pass (i8_prepare)
   DevBuf<uint8_t> xs8_;           // digit image of x1
-  DevBuf<unsigned int> i8_counter_;  // [0] LOSS pass, [1] gradient pass: CTAs counted by the kernels' tails
-  unsigned int i8_counter_total_[2] = {0, 0};
+  DevBuf<unsigned int> i8_counter_;  // [0] LOSS pass, [1] gradient pass, [2] gradient pass (exchange): CTAs counted by the kernels' tails
+  unsigned int i8_counter_total_[3] = {0, 0, 0};
   DevBuf<double> xstats_;         // statistics of x1 gathered while slicing (I8_XSTATS)
   DevBuf<int> rowexp_;            // exponents of the rows of the stored Y (gradient pass)
   int i8_state_ = 0;              // 0 = undecided, 1 = in use, -1 = not used

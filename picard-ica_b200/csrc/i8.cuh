@@ -31,6 +31,7 @@ struct I8LossFinish {
   void* sc = nullptr;             // CoreScalars* (device)
   void* sc_map = nullptr;         // CoreScalars* (pinned host mirror)
   unsigned long long seq = 0;
+  const void* px = nullptr;       // const P2PCall*: exchange the row sums between the ranks inside the kernel (p2p.cuh)
 };
 // LOSS pass at W = L.d_w from the sliced image: one kernel (W' digits, streaming, reduction of the partials into L.d_mom [, loss]).
 // Returns the number of kernels launched.
@@ -40,7 +41,9 @@ int launch_loss_i8(const PassLaunch& L, const uint8_t* xblob, const I8LossFinish
 // (no Hr), tanh / exp densities.  d_rowexp: N ints, e_j with 1.008 |y_jt| < 2^e_j for every t of this shard (i8_row_exponents).
 bool i8_grad_supported(int n, int dens, bool want_h);
 // counter / counter_total as in I8LossFinish (nullptr: partials + a separate reduction launch)
-int launch_grad_i8(const PassLaunch& L, const int* d_rowexp, unsigned int* counter = nullptr, unsigned int* counter_total = nullptr);
+// px: const P2PCall* (exchange [Gr | Sd] between the ranks inside the kernel); counter has three entries then (see CoreSolver)
+int launch_grad_i8(const PassLaunch& L, const int* d_rowexp, unsigned int* counter = nullptr, unsigned int* counter_total = nullptr,
+                   const void* px = nullptr);
 // e_j = bound_exponent(|w_j|_2 * xnorm_max) for the rows of W (n x n): the rigorous bound |y_jt| <= |w_j| |x_t|
 int i8_row_exponents(const double* d_w, int n, const double* d_xstats, int* d_rowexp, cudaStream_t st);
 

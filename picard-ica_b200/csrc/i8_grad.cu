@@ -16,7 +16,7 @@ int i8_row_exponents(const double* d_w, int n, const double* d_xstats, int* d_ro
 }
 
 template <int DENS>
-static int launch_grad_i8_one(const PassLaunch& L, const int* d_rowexp, unsigned int* counter, unsigned int* counter_total) {
+static int launch_grad_i8_one(const PassLaunch& L, const int* d_rowexp, unsigned int* counter, unsigned int* counter_total, const void* px) {
   using G = i8::GradGeom;
   auto kern = i8::grad_i8_kernel<DENS, 0>;
   static PerDeviceInt configured;  // per instantiation and per device
@@ -32,11 +32,15 @@ static int launch_grad_i8_one(const PassLaunch& L, const int* d_rowexp, unsigned
   i8::GradParams p;
   p.n = L.n_out; p.t_local = L.t_local; p.n_tiles = n_tiles; p.dp = make_dens_params(DENS, L.alpha);
   p.rowexp = d_rowexp; p.psi_exp = i8::psi_exponent(DENS, L.alpha); p.partial = L.d_partial;
-  p.counter = nullptr; p.target = 0; p.mom = L.d_mom;
+  p.counter = nullptr; p.target = 0; p.mom = L.d_mom; p.exchange = 0; p.counter2 = nullptr; p.target2 = 0; p.px = P2PCall{};
   if (counter != nullptr && 2 * n_tg <= L.sm_count) {
     // the tail's device-wide wait needs every CTA resident: cooperative launch (one CTA per SM, grid <= SM count)
     *counter_total += (unsigned int)(2 * n_tg);
     p.counter = counter; p.target = *counter_total;
+    if (px) {  // counter[1] / counter_total[1]: the second device-wide count of the exchange
+      counter_total[1] += (unsigned int)(2 * n_tg);
+      p.exchange = 1; p.counter2 = counter + 1; p.target2 = counter_total[1]; p.px = *static_cast<const P2PCall*>(px);
+    }
     long long* no_trace = nullptr;
     void* args[] = {(void*)&tmap, (void*)&p, (void*)&no_trace};
     PICARD_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(2 * n_tg)), dim3(G::NTHREADS), args, G::SMEM_BYTES, L.stream));
@@ -47,11 +51,11 @@ static int launch_grad_i8_one(const PassLaunch& L, const int* d_rowexp, unsigned
   return 1 + rb_reduce(L, (int)n_tg, 2, G::NB, G::MA, true, false, false);
 }
 
-int launch_grad_i8(const PassLaunch& L, const int* d_rowexp, unsigned int* counter, unsigned int* counter_total) {
+int launch_grad_i8(const PassLaunch& L, const int* d_rowexp, unsigned int* counter, unsigned int* counter_total, const void* px) {
   if (L.mode != PASS_GRADY || !i8_grad_supported(L.n_out, L.dens, L.want_h) || L.n_in != L.n_out || L.d_bias != nullptr)
     throw Error(PICARD_COMPUTATION_ERROR, "Computation error: the INT8 gradient pass covers ortho problems with 64 < N <= 128, tanh / exp");
-  return L.dens == DENS_TANH ? launch_grad_i8_one<DENS_TANH>(L, d_rowexp, counter, counter_total)
-                             : launch_grad_i8_one<DENS_EXP>(L, d_rowexp, counter, counter_total);
+  return L.dens == DENS_TANH ? launch_grad_i8_one<DENS_TANH>(L, d_rowexp, counter, counter_total, px)
+                             : launch_grad_i8_one<DENS_EXP>(L, d_rowexp, counter, counter_total, px);
 }
 
 }  // namespace picard

@@ -29,6 +29,7 @@
 #pragma once
 #include "i8.cuh"
 #include "i8_common.cuh"
+#include "p2p.cuh"
 
 namespace picard {
 namespace i8 {
@@ -147,6 +148,12 @@ struct GradParams {
   unsigned int* counter; // nullptr: no tail (the host launches the reduction)
   unsigned int target;
   double* mom;
+  // several GPUs: the exchange of [Gr | Sd] between the ranks happens in the tail as well (compute + reduce + allreduce in ONE kernel):
+  // every CTA pushes its reduced slice into every rank's mailbox; the CTA that completes the local push signals the peers; once
+  // every rank's contribution has arrived each CTA sums its slice over the ranks in rank order.
+  int exchange;
+  unsigned int* counter2; unsigned int target2;   // second device-wide count: "every CTA has pushed"
+  P2PCall px;
 };
 
 #ifndef I8_TRACE_SLOTS
@@ -396,6 +403,7 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
     const int chunk = (total + (int)gridDim.x - 1) / (int)gridDim.x;
     const int lo = (int)blockIdx.x * chunk, hi = lo + chunk < total ? lo + chunk : total;
     constexpr int PSZ = G::NB * G::MA + 3 * G::NB;
+    // element e of the payload lives at mom[e]: Gr (n x n) is followed by Sd (n) in the moment buffer
     for (int e = lo + tid; e < hi; e += G::NTHREADS) {
       const int row = e < nn ? e / n : e - nn;                       // row of Gr / entry of Sd
       const int src = e < nn ? (row & 63) * G::MA + (e - row * n) : G::NB * G::MA + (row & 63);
@@ -407,7 +415,34 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
         for (int u = 0; u < 8; ++u) acc[u] += __ldcg(pp + (size_t)(k + u) * 2 * PSZ);
       }
       for (int u = 0; k < n_tg; ++k, ++u) acc[u] += __ldcg(pp + (size_t)k * 2 * PSZ);
-      p.mom[(e < nn ? mom_off_gr(n) + e : mom_off_sd(n) + row)] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+      const double v = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+      if (!p.exchange) p.mom[e] = v;
+      else
+        for (int q = 0; q < p.px.nranks; ++q) p.px.peers.box[q][p2p_slot(p.px.parity, p.px.rank) + e] = v;
+    }
+    if (p.exchange) {
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        const unsigned int ticket = atomicAdd(p.counter2, 1u);
+        if (ticket + 1u == p.target2) {  // the last CTA of this rank to finish pushing: the rank's contribution is complete everywhere
+          __threadfence_system();
+          for (int q = 0; q < p.px.nranks; ++q)
+            atomicAdd_system(p.px.peers.flags[q] + p.px.parity * P2P_MAX_RANKS + p.px.rank, (unsigned int)P2P_PARTS);
+        }
+      }
+      if (tid < p.px.nranks) {
+        volatile unsigned int* f = p.px.peers.flags[p.px.rank] + p.px.parity * P2P_MAX_RANKS + tid;
+        while ((int)(*f - p.px.expect) < 0) __nanosleep(32);
+        __threadfence_system();
+      }
+      __syncthreads();
+      const double* box = p.px.peers.box[p.px.rank] + p2p_slot(p.px.parity, 0);
+      for (int e = lo + tid; e < hi; e += G::NTHREADS) {
+        double acc = __ldcv(box + e);
+        for (int q = 1; q < p.px.nranks; ++q) acc += __ldcv(box + (size_t)q * P2P_MAX_DOUBLES + e);
+        p.mom[e] = acc;
+      }
     }
   }
 }

@@ -48,6 +48,7 @@ static int launch_loss_i8_one(const PassLaunch& L, const uint8_t* xblob, const I
     *fin.counter_total += (unsigned int)grid;
     tail.counter = fin.counter; tail.target = *fin.counter_total; tail.mom = L.d_mom; tail.finish = fin.finish; tail.which = fin.which;
     if (fin.dims) tail.dims = *static_cast<const CoreDims*>(fin.dims);
+    if (fin.px) { tail.exchange = 1; tail.px = *static_cast<const P2PCall*>(fin.px); }
     tail.signs = fin.signs; tail.sc = static_cast<CoreScalars*>(fin.sc); tail.sc_map = static_cast<CoreScalars*>(fin.sc_map); tail.seq = fin.seq;
   }
   kern<<<(unsigned)grid, G::NTHREADS, G::SMEM_BYTES, L.stream>>>(xblob, p, tail, nullptr);

@@ -28,6 +28,7 @@
 #include "i8.cuh"
 #include "i8_common.cuh"
 #include "loss_point.cuh"
+#include "p2p.cuh"
 
 namespace picard {
 namespace i8 {
@@ -78,6 +79,10 @@ struct LossTail {
   CoreScalars* sc = nullptr;
   CoreScalars* sc_map = nullptr;
   unsigned long long seq = 0;
+  // several GPUs: the 2 n reduced row sums are exchanged over peer memory in this tail too (one-shot: pushed to every rank's
+  // mailbox, summed in rank order on every rank), so a line-search try is ONE launch on any number of GPUs
+  int exchange = 0;
+  P2PCall px{};
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -452,6 +457,30 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const PassParams p, const Loss
           tail.mom[(sec == 0 ? mom_off_sq(p.n_out) : mom_off_ll(p.n_out)) + r] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
       }
       __syncthreads();
+      if (tail.exchange) {
+        const int n = p.n_out;
+        double* seg = tail.mom + mom_off_sq(n);  // [Sq n][L n], contiguous
+        for (int q = 0; q < tail.px.nranks; ++q) {
+          double* slot = tail.px.peers.box[q] + p2p_slot(tail.px.parity, tail.px.rank);
+          for (int i = tid; i < 2 * n; i += G::NTHREADS) slot[i] = seg[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < tail.px.nranks) {
+          atomicAdd_system(tail.px.peers.flags[tid] + tail.px.parity * P2P_MAX_RANKS + tail.px.rank, (unsigned int)P2P_PARTS);
+          volatile unsigned int* f = tail.px.peers.flags[tail.px.rank] + tail.px.parity * P2P_MAX_RANKS + tid;
+          while ((int)(*f - tail.px.expect) < 0) __nanosleep(32);
+          __threadfence_system();
+        }
+        __syncthreads();
+        const double* box = tail.px.peers.box[tail.px.rank] + p2p_slot(tail.px.parity, 0);
+        for (int i = tid; i < 2 * n; i += G::NTHREADS) {
+          double acc = __ldcv(box + i);
+          for (int q = 1; q < tail.px.nranks; ++q) acc += __ldcv(box + (size_t)q * P2P_MAX_DOUBLES + i);
+          seg[i] = acc;
+        }
+        __syncthreads();
+      }
       if (tail.finish && warp == 0) {
         bool sing;
         const double l = small::loss_of_point_warp(tail.dims, tail.mom, tail.signs, &sing);

@@ -18,7 +18,7 @@ int i8_row_exponents(const double* d_w, int n, const double* d_xstats, int* d_ro
 template <int DENS>
 static int launch_grad_i8_one(const PassLaunch& L, const int* d_rowexp, unsigned int* counter, unsigned int* counter_total, const void* px) {
   using G = i8::GradGeom;
-  auto kern = i8::grad_i8_kernel<DENS, 0>;
+  auto kern = i8::grad_i8_kernel<DENS, 0, 1>;  // operand layout 1 (core matrices, no swizzle): 4 % faster than SWIZZLE_32B in profiles/lab
   static PerDeviceInt configured;  // per instantiation and per device
   configured.get([&] {
     PICARD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));

@@ -58,7 +58,8 @@ struct GradGeom {
 // Operand slot layouts (K-major, one 32-byte K-step per row; 8-row groups 256 bytes apart):
 //   LAYOUT 0: SWIZZLE_32B -- rows of 32 bytes, 16-byte chunk c of row r at chunk position c ^ ((r >> 2) & 1)
 //   LAYOUT 1: no swizzle (interleaved core matrices of 8 rows x 16 bytes) -- chunk c of row r at (r >> 3) 256 + c 128 + (r & 7) 16
-// Both are conflict-free for the converters' STS.64; the library uses LAYOUT 0, profiles/lab checks both on the hardware.
+// Both are conflict-free for the converters' STS.64 and both are checked on the hardware by profiles/lab; the library uses LAYOUT 1
+// (measured 5.57 against 5.78 ms at c3).
 template <int LAYOUT>
 __device__ __forceinline__ uint64_t make_desc_k32(uint32_t saddr) {
   uint64_t d = 0;
@@ -333,6 +334,14 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
       if (lane == 0) mbar_arrive(&y_empty[st]);  // the values are in registers: the stage may be refilled
       uint32_t wy[S][2], wp[S];
       digits8(y, sc_y, wy);
+      // the slot is free once the MMAs of tile it - SLOTS have completed; the Y digits go out BEFORE the psi arithmetic, so that
+      // most of this tile's shared-memory writes have completed long before the proxy fence below has to wait for them
+      ptx::mbar_wait(&o_empty[sl], (uint32_t)(((it / G::SLOTS) & 1) ^ 1));
+      if (tr) trace[it * 8 + 6] = clock64();
+      unsigned char* ob = osm + (size_t)sl * G::SLOT_BYTES;
+#pragma unroll
+      for (int pb = 0; pb < S; ++pb)  // byte pb of the fixed-point integer = digit S - 1 - pb
+        *reinterpret_cast<uint2*>(ob + (size_t)(S - 1 - pb) * G::A_DIGIT_BYTES + a_off) = make_uint2(wy[pb][0], wy[pb][1]);
       {
         double psi[4];
         if (NO_PSI) {
@@ -355,15 +364,8 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
         }
         digits4(psi, sc_psi, wp);
       }
-      // the slot is free once the MMAs of tile it - SLOTS have completed
-      ptx::mbar_wait(&o_empty[sl], (uint32_t)(((it / G::SLOTS) & 1) ^ 1));
-      if (tr) trace[it * 8 + 6] = clock64();
-      unsigned char* ob = osm + (size_t)sl * G::SLOT_BYTES;
 #pragma unroll
-      for (int pb = 0; pb < S; ++pb) {  // byte pb of the fixed-point integer = digit S - 1 - pb
-        *reinterpret_cast<uint2*>(ob + (size_t)(S - 1 - pb) * G::A_DIGIT_BYTES + a_off) = make_uint2(wy[pb][0], wy[pb][1]);
-        *reinterpret_cast<uint32_t*>(ob + (size_t)(S - 1 - pb) * G::B_DIGIT_BYTES + b_off) = wp[pb];
-      }
+      for (int pb = 0; pb < S; ++pb) *reinterpret_cast<uint32_t*>(ob + (size_t)(S - 1 - pb) * G::B_DIGIT_BYTES + b_off) = wp[pb];
       ptx::fence_proxy_async();  // generic-proxy stores before the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_full[sl]);

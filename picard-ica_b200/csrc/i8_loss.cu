@@ -51,7 +51,8 @@ static int launch_loss_i8_one(const PassLaunch& L, const uint8_t* xblob, const I
     if (fin.px) { tail.exchange = 1; tail.px = *static_cast<const P2PCall*>(fin.px); }
     tail.signs = fin.signs; tail.sc = static_cast<CoreScalars*>(fin.sc); tail.sc_map = static_cast<CoreScalars*>(fin.sc_map); tail.seq = fin.seq;
   }
-  kern<<<(unsigned)grid, G::NTHREADS, G::SMEM_BYTES, L.stream>>>(xblob, p, tail, nullptr);
+  const CUtensorMap tmap_out = L.d_out != nullptr ? make_tmap_box(L.d_out, L.ld_out, L.t_local, L.n_out, G::CPT, 32, true) : CUtensorMap{};
+  kern<<<(unsigned)grid, G::NTHREADS, G::SMEM_BYTES, L.stream>>>(xblob, tmap_out, p, tail, nullptr);
   PICARD_CUDA(cudaGetLastError());
   if (fin.counter != nullptr) return 1;
   return 1 + rb_reduce(L, (int)grid, 1, 128, 128, false, false, true);

@@ -17,8 +17,8 @@
 //                        publishes the accumulators
 //   warps 0-15         : epilogue, thread = (row = TMEM lane, NT / 4 samples): tcgen05.ld of the 6 levels, accumulators returned
 //                        at once, exact 64-bit combination, scaling by exponent adds, log-likelihood, row sums per thread; Y'
-//                        through a warp-private transpose in shared memory and coalesced 128-bit global stores (no CTA-wide
-//                        barrier: the warps only meet at the accumulator hand-over); warps 0-3 first store W' into tensor memory
+//                        through shared memory and one TMA store per warp and tile of its own [32 rows x 16 samples] box (no
+//                        CTA-wide barrier: the warps only meet at the accumulator hand-over)
 // tanh log-likelihood without a logarithm per element: sum_t [|y| + log(1 + e_t) / a] = sum |y| + log(prod (1 + e_t)) / a with
 // e_t = exp(-2 a |y_t|): the factors lie in [1, 2], so a thread keeps a running product, moves its exponent into an integer counter
 // once per tile and takes ONE logarithm at the end of the kernel (relative error of the product ~ sqrt(#factors) 2^-53).
@@ -53,8 +53,8 @@ struct LossGeom {
   static constexpr int CPT = NT / 4;                               // samples per epilogue thread and tile
   static_assert(CPT % 4 == 0, "tcgen05.ld x4 / x8 granularity");
   static constexpr int NTHREADS = 32 * (NEW + 2);
-  static_assert(CPT == 8 || CPT == 16, "the Y' transpose is written for 4 or 8 chunks per box row");
-  static constexpr size_t SMEM_Y = (size_t)NEW * 32 * CPT * 8;      // one [32 rows x CPT samples] transpose box per epilogue warp
+  static_assert(CPT == 16, "the Y' box row is one 128-byte swizzle row");
+  static constexpr size_t SMEM_Y = (size_t)NEW * 32 * CPT * 8;      // one [32 rows x CPT samples] TMA-store box per epilogue warp
   static constexpr size_t SMEM_B = (size_t)NSTAGE * STAGE_BYTES;
   static constexpr size_t SMEM_A = (size_t)(S - ATM) * SLICE_A_BYTES;
   static constexpr bool BIG = true;                                // the 2048-entry exp table (16 KB); the log table is not needed
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(8 * NT) slice_x_kernel(const double* __restric
 // ---------------------------------------------------------------------------------------------------
 template <int DENS, bool WANT_SQ, int NT, int ABL = 0>
 __global__ void __launch_bounds__(LossGeom<NT>::NTHREADS, 1)  // 18 warps are allocated as 20: 96 registers per thread
-loss_i8_kernel(const uint8_t* __restrict__ xblob, const PassParams p, const LossTail tail, long long* __restrict__ trace) {
+loss_i8_kernel(const uint8_t* __restrict__ xblob, const __grid_constant__ CUtensorMap tmap_out, const PassParams p, const LossTail tail,
+               long long* __restrict__ trace) {
   using G = LossGeom<NT>;
   constexpr int NEW = G::NEW, CPT = G::CPT, NSTAGE = G::NSTAGE;
   constexpr bool BIG = G::BIG;
@@ -361,6 +362,18 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const PassParams p, const Loss
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_empty[st]);
+      // Y' leaves through shared memory and ONE TMA store per warp and tile: box = this warp's [32 rows x CPT samples] (SWIZZLE_128B:
+      // 16-byte chunk c of row r at position c ^ (r & 7), conflict-free for lane = row; the unit clips the ragged last tile and the
+      // rows >= n_out).  The values are written NOW and the store is issued after the density arithmetic below, so that the proxy
+      // fence between the two does not wait for the shared-memory writes (issued right after them it cost 9 % of the epilogue).
+      if (!NO_STORE && p.out != nullptr) {
+        unsigned char* yb = reinterpret_cast<unsigned char*>(ysm) + (size_t)warp * (32 * CPT * 8);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the unit has read the previous tile's box
+        __syncwarp();
+#pragma unroll
+        for (int c2 = 0; c2 < CPT / 2; ++c2)
+          *reinterpret_cast<double2*>(yb + lane * (CPT * 8) + ((c2 ^ (lane & (CPT / 2 - 1))) << 4)) = make_double2(y[2 * c2], y[2 * c2 + 1]);
+      }
       // log-likelihood / y^2 row sums
       if (!NO_DENS) {
         const bool partial_tile = (t0 + CPT > p.t_local);
@@ -391,33 +404,19 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const PassParams p, const Loss
 #pragma unroll
         for (int e = 0; e < CPT; ++e) sl += y[e];
       }
-      // Y' leaves through a warp-private transpose in shared memory and COALESCED 128-bit global stores: a thread owns CPT contiguous
-      // samples of its row (direct stores would touch 32 lines per instruction), so the warp writes its [32 rows x CPT samples] box
-      // (16-byte chunk c of row r at position c ^ swz(r): conflict-free), re-reads it chunk-major and stores 512 contiguous-by-row
-      // bytes per instruction.  Only __syncwarp(): no proxy fence, no TMA store, no CTA-wide barrier on the critical path (the TMA
-      // store path spent ~9 % of the epilogue's time in fence.proxy.async: profiles/summary_r02*.txt).  The Y store's leading
-      // dimension is a multiple of 64 samples, so whole tiles are in bounds; columns >= t_local receive the zero padding of x1.
+      // ... and the TMA store of this warp's box, now that its shared-memory writes (issued before the density arithmetic) have long
+      // completed: the proxy fence finds nothing to wait for
       if (!NO_STORE && p.out != nullptr) {
-        constexpr int CH = CPT / 2;              // 16-byte chunks per box row (8 or 4)
-        constexpr int RPI = 32 / CH;             // rows per store instruction
-        unsigned char* yb = reinterpret_cast<unsigned char*>(ysm) + (size_t)warp * (32 * CPT * 8);
-        __syncwarp();                            // the previous tile's reads of the box are done
-#pragma unroll
-        for (int c2 = 0; c2 < CH; ++c2)
-          *reinterpret_cast<double2*>(yb + lane * (CPT * 8) + ((c2 ^ ((CH == 8 ? lane : (lane >> 1)) & (CH - 1))) << 4)) = make_double2(y[2 * c2], y[2 * c2 + 1]);
+        ptx::fence_proxy_async();
         __syncwarp();
-        const int c2 = lane & (CH - 1);
-        const int64_t tcol = (tile0 + it * tstride) * NT + CPT * cq + 2 * c2;
-#pragma unroll
-        for (int i = 0; i < 32 / RPI; ++i) {
-          const int rr = (lane / CH) + RPI * i;  // row of the box
-          const double2 v = *reinterpret_cast<const double2*>(yb + rr * (CPT * 8) + ((c2 ^ ((CH == 8 ? rr : (rr >> 1)) & (CH - 1))) << 4));
-          const int grow = 32 * q4 + rr;
-          if (grow < p.n_out) *reinterpret_cast<double2*>(p.out + (size_t)grow * p.ld_out + tcol) = v;
+        if (lane == 0) {
+          tma_store_2d(&tmap_out, ysm + (size_t)warp * (32 * CPT), (int)((tile0 + it * tstride) * NT + CPT * cq), 32 * q4);
+          bulk_commit();
         }
       }
       if (tr) trace[it * 8 + 7] = clock64();
     }
+    if (!NO_STORE && p.out != nullptr && lane == 0) bulk_wait0();
     if (DENS == DENS_TANH && !NO_DENS) sl = fma(fma((double)pexp, 6.931471805599453094e-01, log(prod)), p.dp.inv_alpha, sl);
     // the column quarters of a row live in warps q4, q4 + 4, q4 + 8, q4 + 12
     if (cq > 0) { sums[(cq - 1) * 256 + row] = sl; sums[(cq - 1) * 256 + 128 + row] = sq; }

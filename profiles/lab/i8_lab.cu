@@ -103,10 +103,11 @@ static void run_loss(const uint8_t* xblob, const double* w, double* yout, int64_
   using G = i8::LossGeom<I8_TILE>;
   auto kern = i8::loss_i8_kernel<DENS_TANH, false, I8_TILE, ABL>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
+  const CUtensorMap tm = make_tmap_box(yout, ld, t, n, G::CPT, 32, true);
   PassParams p{};
   p.w = w; p.ldw = n; p.n_out = n; p.n_in = n; p.t_local = t; p.n_tiles = (t + I8_TILE - 1) / I8_TILE; p.dp = make_dens_params(DENS_TANH, 1.0); p.partial = partial; p.out = yout; p.ld_out = ld;
   const int grid = sms;
-  float ms = time_ms([&] { kern<<<grid, G::NTHREADS, G::SMEM_BYTES>>>(xblob, p, i8::LossTail{}, d_trace); }, reps);
+  float ms = time_ms([&] { kern<<<grid, G::NTHREADS, G::SMEM_BYTES>>>(xblob, tm, p, i8::LossTail{}, d_trace); }, reps);
   CK(cudaGetLastError());
   printf("{\"kernel\": \"loss_i8\", \"ablation\": %d, \"T\": %lld, \"ms\": %.4f, \"ms_at_1e7\": %.3f}\n", ABL, (long long)t, ms, ms * 1e7 / (double)t);
   if (ABL & 4) {

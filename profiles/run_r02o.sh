@@ -5,5 +5,5 @@ echo "lab exit $?" >> gpurun_out/r02o_lab.err
 timeout -s KILL 600 python -m pytest tests/test_i8_gpu.py -q -m gpu > gpurun_out/r02o_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/r02o_pytest.log
 for f in gpurun_out/r02o_lab.err gpurun_out/r02o_pytest.log; do echo "== $f"; tail -n 4 $f; done
-grep -E "loss_i8|trace.*loss" gpurun_out/r02o_lab.jsonl | cut -c1-200
+grep -E "kernel|trace" gpurun_out/r02o_lab.jsonl | cut -c1-200
 exit 0

@@ -42,10 +42,11 @@ DevCache& dev_cache() { static DevCache* c = new DevCache(); return *c; }  // le
 constexpr size_t kCacheMaxBlock = (size_t)1 << 30, kCacheMaxTotal = (size_t)4 << 30;
 }  // namespace
 
-void* dev_alloc(size_t bytes, size_t* capacity) {
+void* dev_alloc(size_t bytes, size_t* capacity, int* device) {
   const size_t want = (bytes + 511) & ~(size_t)511;
   int dev = 0;
   PICARD_CUDA(cudaGetDevice(&dev));
+  *device = dev;
   if (want <= kCacheMaxBlock) {
     DevCache& c = dev_cache();
     std::lock_guard<std::mutex> lk(c.mu);
@@ -66,11 +67,14 @@ void* dev_alloc(size_t bytes, size_t* capacity) {
   return p;
 }
 
-void dev_free(void* p, size_t capacity) {
+void dev_free(void* p, size_t capacity, int dev) {
   if (!p) return;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != dev) cudaSetDevice(dev);  // the block is filed, synchronised and freed under the device that owns it
+  struct Restore { int cur, dev; ~Restore() { if (cur >= 0 && cur != dev) cudaSetDevice(cur); } } restore{cur, dev};
   if (capacity <= kCacheMaxBlock) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess) {
+    if (cudaDeviceSynchronize() == cudaSuccess) {
       DevCache& c = dev_cache();
       std::lock_guard<std::mutex> lk(c.mu);
       if (c.cached_bytes + capacity <= kCacheMaxTotal) {

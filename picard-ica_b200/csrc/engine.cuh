@@ -33,8 +33,8 @@ void trace_slow(const char* what, size_t bytes, double t0_ms);
 // call after an idle period (50x the whitening kernels they bracket), so blocks up to 1 GiB are kept in a per-device
 // cache (at most 4 GiB in total) and reused; larger blocks (the N x T buffers) go straight to the driver.
 // dev_free synchronises the device first, like cudaFree does, so a block is never reused while work on it is in flight.
-void* dev_alloc(size_t bytes, size_t* capacity);
-void dev_free(void* p, size_t capacity);
+void* dev_alloc(size_t bytes, size_t* capacity, int* device);
+void dev_free(void* p, size_t capacity, int device);  // device: the one the block was allocated on (the cache key)
 void dev_cache_release();  // return every cached block to the driver
 // pinned arena of large `sources` results (fit.cu)
 bool result_arena_release(double* p);  // true if p was the arena: it is free for the next fit
@@ -49,20 +49,21 @@ struct DevBuf {
   explicit DevBuf(size_t count) { alloc(count); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = 0; o.cap = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), cap(o.cap), dev(o.dev) { o.p = nullptr; o.n = 0; o.cap = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = 0; o.cap = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; dev = o.dev; o.p = nullptr; o.n = 0; o.cap = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
   size_t cap = 0;  // bytes of the underlying block (>= sizeof(T) * n: blocks come from the cache below)
+  int dev = 0;     // the device that owns the block
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) p = static_cast<T*>(dev_alloc(sizeof(T) * count, &cap));
+    if (count) p = static_cast<T*>(dev_alloc(sizeof(T) * count, &cap, &dev));
   }
   void release() {
-    if (p) dev_free(p, cap);
+    if (p) dev_free(p, cap, dev);
     p = nullptr; n = 0; cap = 0;
   }
   void zero(cudaStream_t st) { if (p) PICARD_CUDA(cudaMemsetAsync(p, 0, sizeof(T) * n, st)); }
@@ -107,6 +108,9 @@ class CoreSolver {
   // FastICA parallel iterations (ica_par, solver.rs:218-249) on this solver's data: w (n x n, host) in / out
   void fastica(int64_t iters, double* w_host);
   const double* d_w() const { return W_; }
+  // Frees the N x T work buffers of the passes (Y store, digit image of x1) once the loop is finished: the caller is about to
+  // allocate the `sources` buffer and should not need 4 x the input in device memory at that moment.
+  void release_pass_buffers() { ybuf_.release(); ybuf_valid_ = false; xs8_.release(); if (i8_state_ == 1) i8_state_ = 0; }
   const picard_stats_t& stats() const { return stats_; }
   bool converged() const { return converged_; }
   int64_t n_iterations() const { return n_iterations_; }

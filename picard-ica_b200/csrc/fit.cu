@@ -631,6 +631,7 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
       stats.d2h_bytes += (int64_t)sizeof(double) * nc * t_local;
     }
   } else if (!keep_dev) {
+    core.release_pass_buffers();  // Y store + digit image of x1: not needed any more, and `ysrc` is as large as either
     DevBuf<double> ysrc((size_t)nc * ld1);
     stats.kernel_launches += apply_device(wc.data(), nullptr, nc, nc, x1.p, ld1, ysrc.p, ld1, t_local, guard.sm_count, st);
     cudaEvent_t d0, d1;

@@ -246,3 +246,24 @@ def test_rectangular_whitening_and_transform_of_new_data():
     _cmp(res, ref)
     y = Picard.transform(x[:, :777], res)
     np.testing.assert_allclose(y, res.sources[:, :777], atol=1e-9)
+
+
+def test_large_sources_come_from_the_pinned_arena_and_are_correct():
+    """A `sources` result >= 256 MB is handed out from the library's pinned arena (one DMA into the caller's buffer); a second fit
+    while the first result is still alive falls back to malloc + the staged copy; both give the same numbers, and the arena is
+    reused once the first result is released."""
+    import gc
+    n, t = 40, 900_000  # 288 MB of sources
+    x, _, _ = _data.mixture(n, t, seed=12, kind="laplace")
+    w0 = _data.orthogonal(n, 43)
+    cfg = PicardConfig(w_init=w0, max_iter=5)
+    a = Picard.fit_with_config(x, cfg)
+    b = Picard.fit_with_config(x, cfg)          # `a` still owns the arena
+    np.testing.assert_array_equal(a.sources, b.sources)
+    np.testing.assert_allclose(a.sources, a.full_unmixing() @ (x - a.mean[:, None]), rtol=0, atol=1e-9)
+    keep = a.sources[:, :1000].copy()
+    del a
+    gc.collect()
+    c = Picard.fit_with_config(x, cfg)          # the arena is free again
+    np.testing.assert_array_equal(c.sources[:, :1000], keep)
+    np.testing.assert_array_equal(c.sources, b.sources)

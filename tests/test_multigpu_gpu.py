@@ -24,6 +24,14 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+def _density(cfgkw):
+    import picard_ica_b200 as P
+    kw = dict(cfgkw)
+    if "exp_alpha" in kw:
+        kw["density"] = P.DensityType.exp_with_alpha(kw.pop("exp_alpha"))
+    return kw
+
+
 def _worker(rank, world, port, x, w0, cfgkw, out):
     import torch
     import torch.distributed as dist
@@ -36,7 +44,7 @@ def _worker(rank, world, port, x, w0, cfgkw, out):
     try:
         comm = Communicator.from_torch_distributed(rank)
         b, e = shard_range(x.shape[1], rank, world)
-        res = P.Picard.fit_with_config(np.ascontiguousarray(x[:, b:e]), P.PicardConfig(w_init=w0, comm=comm, device=rank, **cfgkw))
+        res = P.Picard.fit_with_config(np.ascontiguousarray(x[:, b:e]), P.PicardConfig(w_init=w0, comm=comm, device=rank, **_density(cfgkw)))
         out.put((rank, res.unmixing, res.whitening, res.mean, res.n_iterations, res.converged, res.sources, (b, e)))
         comm.close()
     finally:
@@ -79,4 +87,38 @@ def test_two_gpu_fit_matches_single_gpu(cfgkw):
             np.testing.assert_allclose(sources, single.sources[:, b:e], atol=1e-6)
         else:
             assert sources.shape == (n, e - b)
+    np.testing.assert_array_equal(got[0][1], got[1][1])  # replicated N x N state is bit-identical across ranks
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("n,t,cfgkw", [(136, 24_000, dict(ortho=False, extended=False, exp_alpha=0.1, max_iter=12)),   # BASELINE configs[3] shape: N > 128, non-ortho, exp(0.1)
+                                       (100, 30_000, dict(max_iter=40))])                                               # the c3 engines (INT8 passes, fused peer exchange)
+def test_two_gpu_large_n_matches_single_gpu(n, t, cfgkw):
+    """Sample-sharded fits at the sizes of the headline configurations against the single-GPU fit of the same data: the non-ortho
+    exp(0.1) row-block FP64 kernels with the Hessian moments (c4 shape), and the INT8 pass kernels whose tails carry the exchange
+    between the ranks over peer memory (c3 shape)."""
+    import torch.multiprocessing as mp
+    import picard_ica_b200 as P
+    from picard_ica_b200.utils import amari_distance
+    x, a, _ = _data.mixture(n, t, seed=31, kind="laplace" if "exp_alpha" in cfgkw else "mixed")
+    w0 = _data.orthogonal(n, 43)
+    single = P.Picard.fit_with_config(x, P.PicardConfig(w_init=w0, **_density(cfgkw)))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, x, w0, cfgkw, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=600) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    ortho = cfgkw.get("ortho", True)
+    for rank, unmixing, whitening, mean, n_it, conv, sources, (b, e) in got:
+        assert abs(n_it - single.n_iterations) <= (1 if ortho else 2)
+        np.testing.assert_allclose(whitening, single.whitening, rtol=1e-8, atol=1e-10)
+        # a fixed number of non-ortho iterations does not converge: compare the iterate, not a separating solution
+        assert amari_distance(unmixing @ whitening, np.linalg.pinv(single.full_unmixing())) <= (1e-6 if ortho else 1e-5)
+        if ortho:
+            np.testing.assert_allclose(sources, single.sources[:, b:e], atol=1e-6)
     np.testing.assert_array_equal(got[0][1], got[1][1])  # replicated N x N state is bit-identical across ranks

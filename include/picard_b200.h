@@ -116,8 +116,9 @@ int picard_abi_version(void);
 /* Number of usable CUDA devices (0 = none: every compute call will fail loudly). */
 int picard_device_count(void);
 const char* picard_status_string(int status); /* Display text of error.rs:44-74 */
-/* The library keeps up to 4 GiB of device memory (temporaries <= 1 GiB each) cached between calls because driver allocator
- * calls are slow on these hosts; this returns it to the driver. */
+/* The library keeps the device buffers of a finished call cached for the next one (up to PICARD_CACHE_MAX_GB, default 60 % of the
+ * device's memory) and one pinned host arena for a large `sources` result, because driver allocator calls are slow on these hosts
+ * (an N x T buffer: 5 - 700 ms to free); this returns all of it to the driver.  The cache is also emptied when an allocation fails. */
 void picard_release_cache(void);
 
 /* ---- config (config.rs) --------------------------------------------------------------------------- */

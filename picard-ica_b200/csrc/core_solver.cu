@@ -39,7 +39,17 @@ struct DevCache {
   size_t cached_bytes = 0;
 };
 DevCache& dev_cache() { static DevCache* c = new DevCache(); return *c; }  // leaked on purpose: no destructor order issues at exit
-constexpr size_t kCacheMaxBlock = (size_t)1 << 30, kCacheMaxTotal = (size_t)4 << 30;
+// Cache limit per process: PICARD_CACHE_MAX_GB if set, else 60 % of the device's memory (blocks of every size are kept: returning an
+// N x T buffer to the driver costs anything between 5 and 700 ms -- profiles/README.md, e2e trace of round 2).
+size_t cache_limit_bytes() {
+  static const size_t limit = [] {
+    if (const char* e = getenv("PICARD_CACHE_MAX_GB")) return (size_t)(atof(e) * 1073741824.0);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (size_t)4 << 30; }
+    return (size_t)(0.6 * (double)total_b);
+  }();
+  return limit;
+}
 }  // namespace
 
 void* dev_alloc(size_t bytes, size_t* capacity, int* device) {
@@ -47,7 +57,7 @@ void* dev_alloc(size_t bytes, size_t* capacity, int* device) {
   int dev = 0;
   PICARD_CUDA(cudaGetDevice(&dev));
   *device = dev;
-  if (want <= kCacheMaxBlock) {
+  {
     DevCache& c = dev_cache();
     std::lock_guard<std::mutex> lk(c.mu);
     auto it = c.free_blocks.lower_bound({dev, want});
@@ -61,7 +71,13 @@ void* dev_alloc(size_t bytes, size_t* capacity, int* device) {
   }
   void* p = nullptr;
   const double t0 = trace_now_ms();
-  PICARD_CUDA(cudaMalloc(&p, want));
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e == cudaErrorMemoryAllocation) {  // the cache may be what is in the way: hand it back and try once more
+    cudaGetLastError();
+    dev_cache_release();
+    e = cudaMalloc(&p, want);
+  }
+  PICARD_CUDA(e);
   trace_slow("cudaMalloc", want, t0);
   *capacity = want;
   return p;
@@ -73,18 +89,16 @@ void dev_free(void* p, size_t capacity, int dev) {
   cudaGetDevice(&cur);
   if (cur != dev) cudaSetDevice(dev);  // the block is filed, synchronised and freed under the device that owns it
   struct Restore { int cur, dev; ~Restore() { if (cur >= 0 && cur != dev) cudaSetDevice(cur); } } restore{cur, dev};
-  if (capacity <= kCacheMaxBlock) {
-    if (cudaDeviceSynchronize() == cudaSuccess) {
-      DevCache& c = dev_cache();
-      std::lock_guard<std::mutex> lk(c.mu);
-      if (c.cached_bytes + capacity <= kCacheMaxTotal) {
-        c.free_blocks.insert({{dev, capacity}, p});
-        c.cached_bytes += capacity;
-        return;
-      }
-    } else {
-      cudaGetLastError();
+  if (cudaDeviceSynchronize() == cudaSuccess) {
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.cached_bytes + capacity <= cache_limit_bytes()) {
+      c.free_blocks.insert({{dev, capacity}, p});
+      c.cached_bytes += capacity;
+      return;
     }
+  } else {
+    cudaGetLastError();
   }
   const double t0 = trace_now_ms();
   cudaFree(p);

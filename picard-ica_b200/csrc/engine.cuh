@@ -30,8 +30,9 @@ bool comm_p2p_next(picard_comm* c, size_t count, P2PCall* out);
 double trace_now_ms();
 void trace_slow(const char* what, size_t bytes, double t0_ms);
 // Device memory for the library's temporaries.  cudaMalloc / cudaFree on the B200 hosts were measured at up to 0.4 s per
-// call after an idle period (50x the whitening kernels they bracket), so blocks up to 1 GiB are kept in a per-device
-// cache (at most 4 GiB in total) and reused; larger blocks (the N x T buffers) go straight to the driver.
+// call after an idle period (50x the whitening kernels they bracket), and returning one N x T buffer to the driver at 5 - 700 ms,
+// so freed blocks of every size are kept in a per-device cache and reused by the next fit (limit: PICARD_CACHE_MAX_GB, default 60 %
+// of the device's memory; handed back by picard_release_cache(), and automatically when an allocation fails).
 // dev_free synchronises the device first, like cudaFree does, so a block is never reused while work on it is in flight.
 void* dev_alloc(size_t bytes, size_t* capacity, int* device);
 void dev_free(void* p, size_t capacity, int device);  // device: the one the block was allocated on (the cache key)

@@ -623,6 +623,7 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
   stats.i8_range = cs.i8_range;
   double* host_sources = nullptr;
   prefault.join();
+  trace.mark("  sources: result buffer ready", st);
   if (d_sources) {
     stats.kernel_launches += apply_device(wc.data(), nullptr, nc, nc, x1.p, ld1, d_sources, lds, t_local, guard.sm_count, st);
     if (!keep_dev) {
@@ -632,8 +633,10 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
     }
   } else if (!keep_dev) {
     core.release_pass_buffers();  // Y store + digit image of x1: not needed any more, and `ysrc` is as large as either
+    trace.mark("  sources: pass buffers released", st);
     DevBuf<double> ysrc((size_t)nc * ld1);
     stats.kernel_launches += apply_device(wc.data(), nullptr, nc, nc, x1.p, ld1, ysrc.p, ld1, t_local, guard.sm_count, st);
+    trace.mark("  sources: Y = W x1", st);
     cudaEvent_t d0, d1;
     PICARD_CUDA(cudaEventCreate(&d0)); PICARD_CUDA(cudaEventCreate(&d1));
     PICARD_CUDA(cudaEventRecord(d0, st));
@@ -644,9 +647,10 @@ void fit_device(const double* d_x, int64_t n_features, int64_t n_samples, int64_
     float ms = 0.f; cudaEventElapsedTime(&ms, d0, d1); stats.d2h_ms += ms;
     cudaEventDestroy(d0); cudaEventDestroy(d1);
     stats.d2h_bytes += (int64_t)sizeof(double) * nc * t_local;
+    trace.mark("  sources: D2H", st);
   }
 
-  trace.mark("sources + D2H", st);
+  trace.mark("sources: buffers freed", st);
   out->n_components = nc; out->n_features = nf; out->n_samples = t_local;
   out->whitening = cfg.whiten ? dup_host(K.data(), K.size()) : nullptr;
   out->unmixing = dup_host(wfull.data(), wfull.size());

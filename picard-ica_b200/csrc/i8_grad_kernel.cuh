@@ -330,8 +330,6 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&y_empty[st]);  // the values are in registers: the stage may be refilled
       uint32_t wy[S][2], wp[S];
       digits8(y, sc_y, wy);
       // the slot is free once the MMAs of tile it - SLOTS have completed; the Y digits go out BEFORE the psi arithmetic, so that
@@ -368,7 +366,11 @@ grad_i8_kernel(const __grid_constant__ CUtensorMap tmap, const GradParams p, lon
       for (int pb = 0; pb < S; ++pb) *reinterpret_cast<uint32_t*>(ob + (size_t)(S - 1 - pb) * G::B_DIGIT_BYTES + b_off) = wp[pb];
       ptx::fence_proxy_async();  // generic-proxy stores before the tensor core's async-proxy reads
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_full[sl]);
+      // The stage goes back to the producer only HERE, after the digit stores that consume every value read from it.  Released right
+      // after the shared-memory loads were issued (round-2 first version), the arrival could overtake loads still in flight on the
+      // sub-partition that also hosts the polling producer warp, and the refill replaced a few rows under them: a tile's worth of
+      // error in G and Sd on about every second launch at T = 1e7 (profiles/lab: i8_lab mode 2 found it, run-to-run bit identity).
+      if (lane == 0) { mbar_arrive(&y_empty[st]); mbar_arrive(&o_full[sl]); }
       if (tr) trace[it * 8 + 7] = clock64();
       ++since_flush;
       if (since_flush == G::FLUSH_TILES || it + 1 == my_tiles) { flush(); since_flush = 0; }

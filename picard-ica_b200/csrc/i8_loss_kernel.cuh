@@ -352,16 +352,14 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const __grid_constant__ CUtens
         }
       }
       if (tr) trace[it * 8 + 6] = clock64();
-      // exponents of this thread's samples (bulk-copied with the tile: wait on its barrier for visibility; complete long ago),
-      // then the ring stage goes back to the producer
+      // exponents of this thread's samples (bulk-copied with the tile: wait on its barrier for visibility; complete long ago)
+      // -- the ring stage goes back to the producer further down, once they have been used
       ptx::mbar_wait(&b_full[st], (uint32_t)((it / NSTAGE) & 1));
       {
         const int* csm = reinterpret_cast<const int*>(sb + (size_t)st * G::STAGE_BYTES + (size_t)S * G::SLICE_B_BYTES) + CPT * cq;
 #pragma unroll
         for (int e = 0; e < CPT; ++e) y[e] = scale_pow2(y[e], rexp + csm[e]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&b_empty[st]);
       // Y' leaves through shared memory and ONE TMA store per warp and tile: box = this warp's [32 rows x CPT samples] (SWIZZLE_128B:
       // 16-byte chunk c of row r at position c ^ (r & 7), conflict-free for lane = row; the unit clips the ragged last tile and the
       // rows >= n_out).  The values are written NOW and the store is issued after the density arithmetic below, so that the proxy
@@ -373,7 +371,19 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const __grid_constant__ CUtens
 #pragma unroll
         for (int c2 = 0; c2 < CPT / 2; ++c2)
           *reinterpret_cast<double2*>(yb + lane * (CPT * 8) + ((c2 ^ (lane & (CPT / 2 - 1))) << 4)) = make_double2(y[2 * c2], y[2 * c2 + 1]);
+      } else {
+        // no Y' store: one shared-memory write that depends on every scaled value, so that the release below still follows the use of
+        // everything read from the stage
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) acc += y[e];
+        reinterpret_cast<volatile double*>(reinterpret_cast<unsigned char*>(ysm) + (size_t)warp * (32 * CPT * 8))[lane] = acc;
       }
+      // The ring stage goes back to the producer only after the shared-memory writes that consume the exponents read from it: an
+      // arrival issued right behind the loads can overtake them while they are in flight (found in the gradient kernel, where the
+      // refill then replaced rows under the loads; see the note there).
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_empty[st]);
       // log-likelihood / y^2 row sums
       if (!NO_DENS) {
         const bool partial_tile = (t0 + CPT > p.t_local);

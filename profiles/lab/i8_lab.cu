@@ -71,6 +71,26 @@ __global__ void naive_g_kernel(const double* y, int n, int64_t ld, int64_t t, do
   if (j == 0) sd[i] = d;
 }
 
+// full-size comparison of two n x t matrices: number of elements that differ by more than tol, the largest difference, the first bad index
+__global__ void compare_kernel(const double* a, int64_t lda, const double* b, int64_t ldb, int n, int64_t t, double tol, unsigned long long* out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)n * t; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / t); const int64_t c = i % t;
+    const double d = fabs(a[(size_t)r * lda + c] - b[(size_t)r * ldb + c]);
+    if (!(d <= tol)) {
+      atomicAdd(&out[0], 1ull);
+      atomicMax(&out[1], (unsigned long long)__double_as_longlong(d));
+      atomicMin(&out[2], (unsigned long long)i);
+    }
+  }
+}
+__global__ void checksum_kernel(const double* a, int64_t lda, int n, int64_t t, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)n * t; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / t); const int64_t c = i % t;
+    acc += (unsigned long long)__double_as_longlong(a[(size_t)r * lda + c]) * (2ull * (unsigned long long)i + 1ull);
+  }
+  atomicAdd(out, acc);
+}
 template <typename F>
 static float time_ms(F&& launch, int reps) {
   cudaEvent_t e0, e1;
@@ -201,12 +221,106 @@ int main(int argc, char** argv) {
   long long bits; memcpy(&bits, &hs[1], 8); double mx2; memcpy(&mx2, &bits, 8);
   printf("{\"kernel\": \"slice_x\", \"ms\": %.3f, \"mean_bound\": %.3f, \"min_row_rms\": %.4f, \"max_norm\": %.3f}\n", ms_slice, hs[0] / T, sqrt(min_ms), sqrt(mx2));
 
-  if (only) {
+  if (only == 1) {
     run_loss<0>(xblob, w, y, ld, T, n, partial, sms, 1, d_trace);
     i8::row_exponent_kernel<<<16, 256>>>(w, n, xstats, rowexp);
     CK(cudaDeviceSynchronize());
     run_grad<0, 0>(y, ld, T, n, rowexp, partial, sms, 1, d_trace);
     printf("{\"done\": 1}\n");
+    return 0;
+  }
+  if (only == 2) {
+    // ---- full-size checks: the stored Y' of every sample against a naive product, run-to-run bit identity of both kernels, and the
+    // gradient of the whole range (accumulator flushes every 512 tiles) against the sum of the gradients of eight sub-ranges (no flush)
+    CK(cudaMalloc(&ynaive, sizeof(double) * n * ld));
+    unsigned long long* d_out; CK(cudaMalloc(&d_out, 64));
+    naive_y_kernel<<<(unsigned)(((int64_t)n * 8192 + 255) / 256), 256>>>(w, x, n, ld, 8192, ynaive);  // warm-up of the context
+    CK(cudaDeviceSynchronize());
+    unsigned long long first_sum = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+      CK(cudaMemset(y, 0xff, sizeof(double) * n * ld));
+      run_loss<0>(xblob, w, y, ld, T, n, partial, sms, 1, d_trace);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemset(d_out, 0, 64));
+      checksum_kernel<<<sms * 8, 256>>>(y, ld, n, T, d_out);
+      unsigned long long h[1]; CK(cudaMemcpy(h, d_out, 8, cudaMemcpyDeviceToHost));
+      if (rep == 0) first_sum = h[0];
+      printf("{\"check\": \"loss_i8 Y' checksum\", \"rep\": %d, \"sum\": \"%016llx\", \"same_as_first\": %s}\n", rep, h[0], h[0] == first_sum ? "true" : "false");
+    }
+    {  // naive product of every sample, in slabs of 2^20 samples through the (n x tc) kernel
+      const int64_t slab = 1 << 20;
+      double* ys; CK(cudaMalloc(&ys, sizeof(double) * n * slab));
+      unsigned long long tot_bad = 0; double worst = 0; long long first_bad = -1;
+      for (int64_t c0 = 0; c0 < T; c0 += slab) {
+        const int64_t tc = std::min<int64_t>(slab, T - c0);
+        naive_y_kernel<<<(unsigned)(((int64_t)n * tc + 255) / 256), 256>>>(w, x + c0, n, ld, tc, ys);
+        unsigned long long init[3] = {0, 0, ~0ull}; CK(cudaMemcpy(d_out, init, 24, cudaMemcpyHostToDevice));
+        compare_kernel<<<sms * 8, 256>>>(ys, tc, y + c0, ld, n, tc, 1e-9, d_out);
+        unsigned long long h[3]; CK(cudaMemcpy(h, d_out, 24, cudaMemcpyDeviceToHost));
+        if (h[0]) {
+          double d; memcpy(&d, &h[1], 8);
+          tot_bad += h[0]; worst = fmax(worst, d);
+          if (first_bad < 0) { first_bad = (long long)(c0 + (long long)(h[2] % (unsigned long long)tc)); printf("{\"bad\": \"first in slab\", \"row\": %lld, \"sample\": %lld}\n", (long long)(h[2] / (unsigned long long)tc), first_bad); }
+        }
+      }
+      printf("{\"check\": \"loss_i8 Y' vs naive f64, all samples\", \"T\": %lld, \"elements_off_by_more_than_1e-9\": %llu, \"worst\": %.3e}\n", (long long)T, tot_bad, worst);
+      CK(cudaFree(ys));
+    }
+    i8::row_exponent_kernel<<<16, 256>>>(w, n, xstats, rowexp);
+    CK(cudaDeviceSynchronize());
+    const int n_tg = (int)std::min<int64_t>(sms / 2, (T + 31) / 32);
+    const size_t psz = (size_t)2 * n_tg * (64 * 128 + 3 * 64);
+    std::vector<double> first, g0, sd0;
+    for (int rep = 0; rep < reps; ++rep) {
+      CK(cudaMemset(partial, 0, sizeof(double) * psz));
+      run_grad<0, 1>(y, ld, T, n, rowexp, partial, sms, 1, d_trace);
+      CK(cudaDeviceSynchronize());
+      std::vector<double> part(psz);
+      CK(cudaMemcpy(part.data(), partial, psz * 8, cudaMemcpyDeviceToHost));
+      size_t diff = 0;
+      if (rep == 0) { first = part; reduce_grad(part, n_tg, n, g0, sd0); }
+      else {
+        const size_t per = 64 * 128 + 3 * 64;
+        int imin = 1 << 30, imax = -1, jmin = 1 << 30, jmax = -1, smin = 1 << 30, smax = -1, cta_min = 1 << 30, cta_max = -1;
+        double worst_g = 0, worst_s = 0;
+        for (size_t i = 0; i < psz; ++i)
+          if (memcmp(&part[i], &first[i], 8) != 0) {
+            ++diff;
+            const int cta = (int)(i / per); const size_t o = i % per;
+            cta_min = std::min(cta_min, cta); cta_max = std::max(cta_max, cta);
+            if (o < 64 * 128) {
+              const int il = (int)(o / 128), j = (int)(o % 128);
+              imin = std::min(imin, il); imax = std::max(imax, il); jmin = std::min(jmin, j); jmax = std::max(jmax, j);
+              worst_g = fmax(worst_g, fabs(part[i] - first[i]));
+            } else { const int k = (int)(o - 64 * 128); smin = std::min(smin, k); smax = std::max(smax, k); worst_s = fmax(worst_s, fabs(part[i] - first[i])); }
+          }
+        if (diff) printf("{\"diff\": \"where\", \"rep\": %d, \"cta\": [%d, %d], \"i_local\": [%d, %d], \"j\": [%d, %d], \"tail_index\": [%d, %d], \"worst_g\": %.3e, \"worst_tail\": %.3e}\n",
+                         rep, cta_min, cta_max, imin, imax, jmin, jmax, smin, smax, worst_g, worst_s);
+      }
+      printf("{\"check\": \"grad_i8 partials, run-to-run\", \"rep\": %d, \"values_differing_from_first\": %zu}\n", rep, diff);
+    }
+    {
+      const int chunks = 8;
+      const int64_t cl = ((T / chunks + 31) / 32) * 32;
+      std::vector<double> gs((size_t)n * n, 0.0), sds(n, 0.0);
+      for (int64_t c0 = 0; c0 < T; c0 += cl) {
+        const int64_t tc = std::min<int64_t>(cl, T - c0);
+        const int ntg = (int)std::min<int64_t>(sms / 2, (tc + 31) / 32);
+        CK(cudaMemset(partial, 0, sizeof(double) * psz));
+        run_grad<0, 1>(y + c0, ld, tc, n, rowexp, partial, sms, 1, d_trace);
+        CK(cudaDeviceSynchronize());
+        std::vector<double> part((size_t)2 * ntg * (64 * 128 + 3 * 64)), g, sd;
+        CK(cudaMemcpy(part.data(), partial, part.size() * 8, cudaMemcpyDeviceToHost));
+        reduce_grad(part, ntg, n, g, sd);
+        for (size_t i = 0; i < g.size(); ++i) gs[i] += g[i];
+        for (int i = 0; i < n; ++i) sds[i] += sd[i];
+      }
+      double num = 0, den = 0, nsd = 0, dsd = 0;
+      for (size_t i = 0; i < gs.size(); ++i) { num = fmax(num, fabs(g0[i] - gs[i])); den = fmax(den, fabs(gs[i])); }
+      for (int i = 0; i < n; ++i) { nsd = fmax(nsd, fabs(sd0[i] - sds[i])); dsd = fmax(dsd, fabs(sds[i])); }
+      printf("{\"check\": \"grad_i8 whole range vs sum of 8 sub-ranges\", \"T\": %lld, \"gr_rel\": %.3e, \"sd_rel\": %.3e}\n", (long long)T, num / den, nsd / dsd);
+    }
+    printf("{\"done\": 2}\n");
     return 0;
   }
   // ---- LOSS kernel: timing, ablations, trace

@@ -61,7 +61,8 @@ WORKLOADS = {
 FP64_PEAK_FALLBACK_TFLOPS = 37.19  # round-1 microbenchmark (profiles/microbench/fp64_pipes_r01.jsonl); used only if the in-run probe fails
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at c3 on one GPU, from the committed ncu --set full captures (None = not
 # captured for the current kernel).  Scaled to the rank's share of the samples; reported with its source, never silently.
-NCU_TRAFFIC_C3 = {"loss": (None, None), "grady": (None, None)}
+NCU_TRAFFIC_C3 = {"loss": (7.721367e9 + 10.192575e9, "profiles/summary_r02y.txt (ncu --set full of loss_i8_kernel inside this bench command, one GPU, T = 1e7)"),
+                  "grady": (10.327482e9 + 0.091629e9, "profiles/summary_r02z.txt (ncu --set full of grad_i8_kernel inside this bench command, one GPU, T = 1e7)")}
 
 
 class ClockSampler(threading.Thread):

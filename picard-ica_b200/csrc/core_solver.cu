@@ -32,6 +32,27 @@ void trace_slow(const char* what, size_t bytes, double t0_ms) {
   if (dt > 5.0) fprintf(stderr, "[picard trace]     slow %s of %.1f MB: %.1f ms\n", what, bytes / 1048576.0, dt);
 }
 
+// PICARD_TRACE_GAPS diagnostics: host time between the moment the scalars of a kernel arrive and the moment the next kernel of the
+// dependent chain has been handed to the driver (the GPU idles for at least that long), per kind of hand-over.
+struct GapProbe {
+  bool on = getenv("PICARD_TRACE_GAPS") != nullptr;
+  double last_exit = -1.0, acc[4] = {0, 0, 0, 0}, wait_ms = 0.0;
+  long n[4] = {0, 0, 0, 0}, waits = 0;
+  static double now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  void launched(int kind) {
+    if (!on || last_exit < 0) return;
+    acc[kind] += now() - last_exit; ++n[kind]; last_exit = -1.0;
+  }
+  void report() {
+    if (!on) return;
+    const char* names[4] = {"front -> transforms enqueued", "rejected try -> next LOSS enqueued", "accepted try -> gradient enqueued", "other"};
+    for (int k = 0; k < 4; ++k)
+      if (n[k]) fprintf(stderr, "[picard gaps] %-36s %8.2f us avg over %ld\n", names[k], 1e3 * acc[k] / n[k], n[k]);
+    if (waits) fprintf(stderr, "[picard gaps] %-36s %8.2f us avg over %ld\n", "host wait for scalars", 1e3 * wait_ms / waits, waits);
+  }
+};
+static thread_local GapProbe g_gaps;
+
 namespace {
 struct DevCache {
   std::mutex mu;
@@ -288,6 +309,7 @@ bool CoreSolver::eval_pass(const double* d_w, int mode, bool want_h, int dens, d
     stats_.i8_grad_passes++;
   }
   else stats_.kernel_launches += launch_pass(L);
+  g_gaps.launched(mode == PASS_LOSS ? 1 : (mode == PASS_GRADY ? 2 : 3));
   PICARD_CUDA(cudaEventRecord(ev_b_, st_));
   // one allreduce of exactly what this pass produced -- unless the pass kernel has carried the exchange itself
   if (comm_ && comm_size(comm_) > 1 && !exchanged) {
@@ -310,6 +332,8 @@ bool CoreSolver::pass(const double* d_w, int mode, double* d_mom, int finish_whi
 // host mirror and then the sequence number: spin on it instead of a D2H copy + stream synchronisation.
 void CoreSolver::fetch_scalars() {
   volatile CoreScalars* h = sc_host_.p;
+  const double g0 = g_gaps.on ? GapProbe::now() : 0.0;
+  struct GapExit { double g0; ~GapExit() { if (g_gaps.on) { g_gaps.last_exit = GapProbe::now(); g_gaps.wait_ms += g_gaps.last_exit - g0; ++g_gaps.waits; } } } gap_exit{g0};
   for (uint64_t spins = 1; h->seq != seq_; ++spins) {
 #if defined(__x86_64__)
     __builtin_ia32_pause();
@@ -364,6 +388,7 @@ void CoreSolver::try_point(double alpha, bool speculate, int try_index, int trie
       const int r = small::matrix_exp_candidates(D_, alpha, sc_host_.p->norm_d, n, tries_planned < 4 ? tries_planned : 4, ew_, W_, wt_all_.p, st_);
       cand_ready_ = r > 0 ? r : 0;
       if (r > 0) stats_.kernel_launches += 1;
+      g_gaps.launched(0);
     }
     if (try_index < cand_ready_) w_try_ = wt_all_.p + (size_t)try_index * n * n;
     else stats_.kernel_launches += small::matrix_exp(D_, alpha, sc_host_.p->norm_d, n, ew_, nullptr, st_, W_, Wt_);
@@ -488,6 +513,7 @@ int64_t CoreSolver::run(int64_t max_new) {
   float ms = 0.f;
   PICARD_CUDA(cudaEventElapsedTime(&ms, ev_run0_, ev_run1_));
   stats_.core_ms += ms;
+  g_gaps.report();
   return done;
 }
 

@@ -43,8 +43,34 @@ struct GapProbe {
     if (!on || last_exit < 0) return;
     acc[kind] += now() - last_exit; ++n[kind]; last_exit = -1.0;
   }
+  // device time of the N x N kernels between the passes (events on the solver's stream, read back after the next wait)
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double dev_ms[2] = {0, 0};
+  long dev_n[2] = {0, 0};
+  int pending = -1;
+  void dev_begin(int kind, cudaStream_t st) {
+    if (!on) return;
+    if (!ev[0]) for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[2 * kind], st);
+  }
+  void dev_end(int kind, cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(ev[2 * kind + 1], st);
+    pending = kind;
+  }
+  void dev_collect() {
+    if (!on || pending < 0) return;
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev[2 * pending + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, ev[2 * pending], ev[2 * pending + 1]) == cudaSuccess) {
+      dev_ms[pending] += ms; ++dev_n[pending];
+    }
+    pending = -1;
+  }
   void report() {
     if (!on) return;
+    const char* dn[2] = {"device: transforms (expm + W' products)", "device: gradient end -> front done"};
+    for (int k = 0; k < 2; ++k)
+      if (dev_n[k]) fprintf(stderr, "[picard gaps] %-36s %8.2f us avg over %ld\n", dn[k], 1e3 * dev_ms[k] / dev_n[k], dev_n[k]);
     const char* names[4] = {"front -> transforms enqueued", "rejected try -> next LOSS enqueued", "accepted try -> gradient enqueued", "other"};
     for (int k = 0; k < 4; ++k)
       if (n[k]) fprintf(stderr, "[picard gaps] %-36s %8.2f us avg over %ld\n", names[k], 1e3 * acc[k] / n[k], n[k]);
@@ -333,7 +359,7 @@ bool CoreSolver::pass(const double* d_w, int mode, double* d_mom, int finish_whi
 void CoreSolver::fetch_scalars() {
   volatile CoreScalars* h = sc_host_.p;
   const double g0 = g_gaps.on ? GapProbe::now() : 0.0;
-  struct GapExit { double g0; ~GapExit() { if (g_gaps.on) { g_gaps.last_exit = GapProbe::now(); g_gaps.wait_ms += g_gaps.last_exit - g0; ++g_gaps.waits; } } } gap_exit{g0};
+  struct GapExit { double g0; ~GapExit() { if (g_gaps.on) { g_gaps.dev_collect(); g_gaps.last_exit = GapProbe::now(); g_gaps.wait_ms += g_gaps.last_exit - g0; ++g_gaps.waits; } } } gap_exit{g0};
   for (uint64_t spins = 1; h->seq != seq_; ++spins) {
 #if defined(__x86_64__)
     __builtin_ia32_pause();
@@ -385,7 +411,9 @@ void CoreSolver::try_point(double alpha, bool speculate, int try_index, int trie
       if (!wt_all_.p) wt_all_.alloc((size_t)small::EXPM_NC * n * n);
       // the first candidates only: 95 % of the line searches end within four tries (2.4 on average at c3), and every candidate costs
       // one more N x N x N product in the kernel; later tries take the per-try kernel (same bits)
+      g_gaps.dev_begin(0, st_);
       const int r = small::matrix_exp_candidates(D_, alpha, sc_host_.p->norm_d, n, tries_planned < 4 ? tries_planned : 4, ew_, W_, wt_all_.p, st_);
+      g_gaps.dev_end(0, st_);
       cand_ready_ = r > 0 ? r : 0;
       if (r > 0) stats_.kernel_launches += 1;
       g_gaps.launched(0);
@@ -451,7 +479,9 @@ int64_t CoreSolver::run(int64_t max_new) {
     fa.signs = signs_; fa.old_signs = old_signs_; fa.S_prev = Sprev_; fa.mem_s = mem_s_; fa.mem_y = mem_y_; fa.mem_r = mem_r_;
     fa.q = q_; fa.D = D_; fa.sc = sc_dev_.p; fa.first_iter = (iter_ == 0) ? 1 : 0; fa.do_lbfgs = 1;
     fa.sc_map = sc_host_.p; fa.seq = next_seq();
+    g_gaps.dev_begin(1, st_);
     stats_.kernel_launches += small::iteration_front(fa, st_);
+    g_gaps.dev_end(1, st_);
     fetch_scalars();
     gradient_norm_ = sc_host_.p->gradient_norm;
     if (sc_host_.p->sign_change) stats_.sign_changes++;

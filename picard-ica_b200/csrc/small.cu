@@ -274,6 +274,310 @@ __global__ void __launch_bounds__(BT1) front_kernel(FrontArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same iteration front on ONE THREAD-BLOCK CLUSTER of 16 CTAs (n <= 128, m <= 7): every matrix element is owned by one
+// thread for the whole kernel (CTA = 8 rows, warp = one row, lane = 4 consecutive columns), so G, H, q, D and the whole L-BFGS
+// history live in registers; what the single-CTA kernel above re-reads from L2 in ~45 dependent sweeps (100 us at n = 128) is
+// loaded once.  Values at the transposed position that are plain functions of the raw moments (G^T, H^T, hoff_j, sign_j) are
+// recomputed from the moments instead of exchanged; the one genuine exchange (q^T for the preconditioner) goes through L2
+// behind a cluster barrier.  Dot products and maxima: warp shuffles, 8 per-warp partials in shared memory, the CTA's partial
+// pushed into every CTA's slot array over distributed shared memory, one cluster barrier, a fixed-order sum of the 16 slots
+// (identical on every CTA).  Same formulas and the same per-element operation order as front_kernel; only the order of the
+// reductions differs (last-bit differences in the dot products).
+// ---------------------------------------------------------------------------------------------------
+constexpr int FC_CTAS = 16, FC_THREADS = 256, FC_M = 7;
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dsmem_store(double* local_addr, uint32_t target_rank, double v) {
+  uint32_t la = (uint32_t)__cvta_generic_to_shared(local_addr), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(target_rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+struct ClusterRed {
+  double slot[2][2][FC_CTAS];  // [buffer][value][source CTA]
+  double warp[2][8];           // [value][warp] partials of this CTA
+};
+// Reduces two values over the whole cluster: value 0 with + (SUM0) or fmax, value 1 always with fmax.  Every thread returns the
+// same bits.  One cluster barrier; the slot buffers alternate so that no barrier is needed after the final reads.
+template <bool SUM0>
+__device__ __forceinline__ void cluster_reduce2(double& v0, double& v1, ClusterRed* cr, int& buf, uint32_t rank) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const double p0 = __shfl_xor_sync(0xffffffffu, v0, o), p1 = __shfl_xor_sync(0xffffffffu, v1, o);
+    v0 = SUM0 ? v0 + p0 : fmax(v0, p0);
+    v1 = fmax(v1, p1);
+  }
+  if (lane == 0) { cr->warp[0][warp] = v0; cr->warp[1][warp] = v1; }
+  __syncthreads();
+  if (warp == 0 && lane < FC_CTAS) {
+    double c0 = cr->warp[0][0], c1 = cr->warp[1][0];
+#pragma unroll
+    for (int w = 1; w < FC_THREADS / 32; ++w) { c0 = SUM0 ? c0 + cr->warp[0][w] : fmax(c0, cr->warp[0][w]); c1 = fmax(c1, cr->warp[1][w]); }
+    dsmem_store(&cr->slot[buf][0][rank], (uint32_t)lane, c0);
+    dsmem_store(&cr->slot[buf][1][rank], (uint32_t)lane, c1);
+  }
+  cluster_sync_all();
+  double r0 = cr->slot[buf][0][0], r1 = cr->slot[buf][1][0];
+#pragma unroll
+  for (int c = 1; c < FC_CTAS; ++c) { r0 = SUM0 ? r0 + cr->slot[buf][0][c] : fmax(r0, cr->slot[buf][0][c]); r1 = fmax(r1, cr->slot[buf][1][c]); }
+  v0 = r0; v1 = r1;
+  buf ^= 1;
+}
+
+__global__ void __cluster_dims__(FC_CTAS, 1, 1) __launch_bounds__(FC_THREADS, 1) front_cluster_kernel(FrontArgs a) {
+  __shared__ ClusterRed cr;
+  const int n = a.d.n, nn = n * n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, m = a.d.m;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0 && tid == 0;
+  const double tf = a.d.t_total, lam = a.d.lambda_min;
+  const bool ortho = a.d.ortho != 0, ext = a.d.extended != 0;
+  const double* Gr = a.mom + mom_off_gr(n);
+  const double* Hr = a.mom + mom_off_hr(n);
+  const double* Sd = a.mom + mom_off_sd(n);
+  const double* Sq = a.mom + mom_off_sq(n);
+  const int i = 8 * (int)rank + warp, j0 = 4 * lane;  // this thread: row i, columns j0 .. j0 + 3
+  const bool rowok = i < n;
+  bool ok[4];
+  int e[4], et[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    ok[u] = rowok && (j0 + u) < n;
+    e[u] = ok[u] ? i * n + j0 + u : 0;
+    et[u] = ok[u] ? (j0 + u) * n + i : 0;
+  }
+  int rbuf = 0;
+  // ring state before this launch (read by every thread BEFORE the first cluster barrier; the leader rewrites it after it)
+  int len = a.sc->mem_len, head = a.sc->mem_head;
+  const int have_prev = a.sc->have_prev_step, have_old = a.sc->have_g_old;
+
+  double G[4], H[4], HT[4], hoff_i = 1.0, hoff_j[4];
+  int new_slot = -1;
+  double new_r = 0.0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { G[u] = 0.0; H[u] = 1.0; HT[u] = 1.0; hoff_j[u] = 1.0; }
+
+  if (a.do_lbfgs != 2) {
+    // ---- signs of the own row and of the own columns (core.rs:225-237), straight from the moments
+    double sgn_i = 1.0, sgn_j[4] = {1.0, 1.0, 1.0, 1.0}, pm_i = 0.0, pm_j[4] = {0.0, 0.0, 0.0, 0.0};
+    double change = 0.0;
+    if (rowok) {
+      pm_i = Sd[i] / tf;
+      if (ext) {
+        const double gii = Gr[i * n + i] / tf;
+        sgn_i = rust_signum(pm_i * a.C[i * n + i] - gii);
+        if (!a.first_iter && sgn_i != a.old_signs[i]) change = 1.0;
+      }
+    }
+    __syncwarp();  // every lane has read old_signs[i] before lane 0 overwrites it
+    if (rowok && lane == 0) {
+      a.signs[i] = sgn_i;
+      if (ext) a.old_signs[i] = sgn_i;
+    }
+    double gt[4] = {0, 0, 0, 0}, gtT[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const int j = j0 + u;
+      pm_j[u] = Sd[j] / tf;
+      const double gjj_raw = Gr[j * n + j] / tf;
+      if (ext) sgn_j[u] = rust_signum(pm_j[u] * a.C[j * n + j] - gjj_raw);
+      // g = Gr / T, sign-scaled rows, + C when not ortho (core.rs:218, 240-252)
+      double v = Gr[e[u]] / tf;
+      if (ext) { v *= sgn_i; if (!ortho) v = v + a.C[e[u]]; }
+      gt[u] = v;
+      a.Gtmp[e[u]] = v;
+      double vjj = gjj_raw;
+      if (ext) { vjj *= sgn_j[u]; if (!ortho) vjj = vjj + a.C[j * n + j]; }
+      hoff_j[u] = ortho ? vjj : 1.0;                                   // core.rs:256-260
+      if (ortho) { double vt = Gr[et[u]] / tf; if (ext) vt *= sgn_j[u]; gtT[u] = vt; }
+    }
+    if (rowok) {
+      double vii = Gr[i * n + i] / tf;
+      if (ext) { vii *= sgn_i; if (!ortho) vii = vii + a.C[i * n + i]; }
+      hoff_i = ortho ? vii : 1.0;
+      if (lane == 0) a.hoff[i] = hoff_i;
+    }
+    // ---- Hessian approximation (core.rs:263-277) and regularize_hessian (lbfgs.rs:155-171: per unordered pair, (lo,hi) then (hi,lo))
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const int j = j0 + u;
+      if (ortho) {
+        const double pmi = (ext ? sgn_i : 1.0) * pm_i, pmj = (ext ? sgn_j[u] : 1.0) * pm_j[u];
+        H[u] = fmax(0.5 * (pmi + pmj - hoff_i - hoff_j[u]), lam);
+        HT[u] = H[u];
+      } else {
+        const double he = ext ? (sgn_i * Hr[e[u]] + Sq[j]) / tf : Hr[e[u]] / tf;
+        const double ht = ext ? (sgn_j[u] * Hr[et[u]] + Sq[i]) / tf : Hr[et[u]] / tf;
+        if (i == j) { H[u] = he; HT[u] = he; }
+        else {
+          double hij = i < j ? he : ht, hji = i < j ? ht : he;  // (lo,hi) and (hi,lo)
+          const double four = i < j ? 4.0 * hoff_i * hoff_j[u] : 4.0 * hoff_j[u] * hoff_i;
+          {
+            const double diff = hij - hji, discr = sqrt(diff * diff + four), ev = 0.5 * (hij + hji - discr);
+            if (ev < lam) hij += lam - ev;
+          }
+          {
+            const double diff = hji - hij, discr = sqrt(diff * diff + four), ev = 0.5 * (hji + hij - discr);
+            if (ev < lam) hji += lam - ev;
+          }
+          H[u] = i < j ? hij : hji;
+          HT[u] = i < j ? hji : hij;
+        }
+      }
+      a.H[e[u]] = H[u];
+    }
+    // ---- projection (core.rs:280-286) and norm (core.rs:289)
+    double mx = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const int j = j0 + u;
+      double v;
+      if (ortho) v = (gt[u] - gtT[u]) / 2.0;
+      else v = (i == j) ? gt[u] - 1.0 : gt[u];
+      G[u] = v;
+      a.G[e[u]] = v;
+      mx = fmax(mx, fabs(v));
+    }
+    cluster_reduce2<false>(mx, change, &cr, rbuf, rank);
+    const double gnorm = mx;
+    const int sign_change = change != 0.0 ? 1 : 0;
+    if (leader) { a.sc->gradient_norm = gnorm; a.sc->sign_change = sign_change; }
+    if (!a.do_lbfgs) return;
+
+    // ---- L-BFGS memory update (core.rs:296-314, quirk Q9)
+    if (!a.first_iter && have_prev && have_old) {
+      double yd[4], sp[4], part = 0.0, zero = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        yd[u] = 0.0; sp[u] = 0.0;
+        if (!ok[u]) continue;
+        yd[u] = G[u] - a.G_old[e[u]];
+        sp[u] = a.S_prev[e[u]];
+        part += sp[u] * yd[u];
+      }
+      cluster_reduce2<true>(part, zero, &cr, rbuf, rank);
+      const double r = 1.0 / part;
+      if (isfinite(r)) {
+        int slot;
+        if (len < m) { slot = (head + len) % m; ++len; }
+        else { slot = head; head = (head + 1) % m; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ok[u]) { a.mem_s[(size_t)slot * nn + e[u]] = sp[u]; a.mem_y[(size_t)slot * nn + e[u]] = yd[u]; }
+        if (leader) a.mem_r[slot] = r;
+        new_slot = slot; new_r = r;
+      }
+      if (leader) { a.sc->have_prev_step = 0; a.sc->last_r = r; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (ok[u]) a.G_old[e[u]] = G[u];
+    // ---- sign change: loss with the new signs, flush memory (core.rs:317-331, quirk Q11)
+    if (ext && sign_change) {
+      if (leader) {
+        // the leader's own row-0 sign is in place; the other rows' signs were written by other CTAs before the barrier of the
+        // first reduction, which every CTA has passed
+        bool sing;
+        const double l = loss_of_point(a.d, a.mom, a.signs, &sing);
+        a.sc->current_loss = l;  // singular -> 1e15 and continue
+      }
+      len = 0; head = 0;
+    }
+    if (leader) { a.sc->mem_len = len; a.sc->mem_head = head; a.sc->have_g_old = 1; }
+  } else {
+    // direction only (test hook): G, H, hoff are in place
+    if (rowok) hoff_i = a.hoff[i];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (ok[u]) { G[u] = a.G[e[u]]; H[u] = a.H[e[u]]; HT[u] = a.H[et[u]]; hoff_j[u] = a.hoff[j0 + u]; }
+  }
+
+  // ---- direction: two-loop recursion (lbfgs.rs:84-133) with the whole history in registers
+  double sk[FC_M][4], yk[FC_M][4], rk[FC_M], alist[FC_M];
+#pragma unroll
+  for (int k = 0; k < FC_M; ++k) {
+    rk[k] = 0.0; alist[k] = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { sk[k][u] = 0.0; yk[k][u] = 0.0; }
+    if (k < len) {
+      const int slot = (head + k) % m;
+      rk[k] = slot == new_slot ? new_r : a.mem_r[slot];  // the pair pushed by this launch: r is known to every thread, and each thread
+#pragma unroll                                            // reads back only the elements it wrote itself
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) { sk[k][u] = a.mem_s[(size_t)slot * nn + e[u]]; yk[k][u] = a.mem_y[(size_t)slot * nn + e[u]]; }
+    }
+  }
+  double q[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) q[u] = G[u];
+#pragma unroll
+  for (int k = FC_M - 1; k >= 0; --k) {
+    if (k >= len) continue;  // uniform over the cluster
+    double part = 0.0, zero = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) part += sk[k][u] * q[u];
+    cluster_reduce2<true>(part, zero, &cr, rbuf, rank);
+    const double al = rk[k] * part;
+    alist[k] = al;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = q[u] - al * yk[k][u];
+  }
+  // preconditioner: the value at the transposed position belongs to another CTA -> one exchange through L2
+  double D[4];
+  if (ortho) {
+    double gq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { gq[u] = ok[u] ? q[u] / H[u] : 0.0; if (ok[u]) a.Gtmp[e[u]] = gq[u]; }
+    __threadfence();
+    cluster_sync_all();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) D[u] = ok[u] ? (gq[u] - __ldcg(a.Gtmp + et[u])) / 2.0 : 0.0;
+  } else {  // solve_hessian_system (lbfgs.rs:136-150, quirk Q15)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (ok[u]) a.q[e[u]] = q[u];
+    __threadfence();
+    cluster_sync_all();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      D[u] = 0.0;
+      if (!ok[u]) continue;
+      const double qt = __ldcg(a.q + et[u]);
+      const double det = H[u] * HT[u] - hoff_i * hoff_j[u];
+      if (fabs(det) > 1e-15) D[u] = (HT[u] * q[u] - hoff_i * qt) / det;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < FC_M; ++k) {
+    if (k >= len) continue;
+    double part = 0.0, zero = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) part += yk[k][u] * D[u];
+    cluster_reduce2<true>(part, zero, &cr, rbuf, rank);
+    const double beta = rk[k] * part;
+    const double cf = alist[k] - beta;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) D[u] = D[u] + cf * sk[k][u];
+  }
+  double dm = 0.0, zero = 0.0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const double v = -D[u];
+    if (ok[u]) { a.D[e[u]] = v; dm = fmax(dm, fabs(v)); }
+  }
+  cluster_reduce2<false>(dm, zero, &cr, rbuf, rank);
+  if (leader) {
+    a.sc->norm_d = dm;
+    publish_scalars(a.sc, a.sc_map, a.seq);
+  }
+}
+
 __global__ void loss_kernel(CoreDims d, const double* mom, const double* signs, CoreScalars* sc, int which, CoreScalars* sc_map,
                             unsigned long long seq) {
   bool sing;
@@ -376,7 +680,7 @@ constexpr int EXPM_MAX_CTAS = 32;
 // acc[t][e] (t < 4) += T (8 x n, shared, pitch P) * B (n x n, global; element transform (b * mul0) * mul1) for column blocks
 // cb = warp + 8 t; thread (j, c): rows c, columns 8 cb + 2 j + e.  B may have been written by other CTAs: plain coherent loads.
 // ldb: leading dimension of B (n for global matrices, the padded pitch for the shared-memory copy of A_s).
-__device__ __forceinline__ void rows_times(const double* T, int P, const double* B, int ldb, int n, double mul0, double mul1, double acc[4][2]) {
+__device__ __forceinline__ void rows_times_general(const double* T, int P, const double* B, int ldb, int n, double mul0, double mul1, double acc[4][2]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = lane & 3, c = lane >> 2;
   const int ncb = (n + 7) >> 3;
 #pragma unroll
@@ -398,11 +702,52 @@ __device__ __forceinline__ void rows_times(const double* T, int P, const double*
   }
 }
 
+// The same product when n is a multiple of 8 and B needs no scaling (A_s copied to shared memory, or W): no bounds logic, no
+// per-element address arithmetic -- the general loop above spends ~40 integer instructions per DMMA, which is what bound the
+// transform kernels (ncu: DMMA pipe 16 % busy).  NV = number of valid column blocks of this warp (warp-uniform).  Same DMMA
+// sequence per accumulator as the general loop: bit-identical results.
+template <int NV>
+__device__ __forceinline__ void rows_times_dense(const double* __restrict__ T, int P, const double* B, int ldb, int n, double acc[4][2]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = lane & 3, c = lane >> 2;
+  const double* ap = T + c * P + j;
+  const double* bp = B + (size_t)j * ldb + 8 * warp + c;
+  const size_t kstep = (size_t)4 * ldb;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll 8
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    const double a = ap[k0];
+    double b[NV];
+#pragma unroll
+    for (int t = 0; t < NV; ++t) b[t] = bp[64 * t];
+    bp += kstep;
+#pragma unroll
+    for (int t = 0; t < NV; ++t)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a), "d"(b[t]));
+  }
+}
+__device__ __forceinline__ void rows_times(const double* T, int P, const double* B, int ldb, int n, double mul0, double mul1, double acc[4][2]) {
+  if ((n & 7) == 0 && mul0 == 1.0 && mul1 == 1.0) {  // uniform over the grid
+    const int warp = threadIdx.x >> 5, ncb = n >> 3;
+    const int nv = warp < ncb ? (ncb - warp + 7) >> 3 : 0;  // column blocks warp, warp + 8, ... < ncb
+    switch (nv) {
+      case 1: rows_times_dense<1>(T, P, B, ldb, n, acc); break;
+      case 2: rows_times_dense<2>(T, P, B, ldb, n, acc); break;
+      case 3: rows_times_dense<3>(T, P, B, ldb, n, acc); break;
+      case 4: rows_times_dense<4>(T, P, B, ldb, n, acc); break;
+      default:
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+    }
+    return;
+  }
+  rows_times_general(T, P, B, ldb, n, mul0, mul1, acc);
+}
+
 __global__ void __launch_bounds__(256) expm_rows_kernel(const double* __restrict__ D, double alpha, double inv_scale, double first_norm, int s,
                                                         int n, double* flags, unsigned int* bar, double* Rg0, double* Rg1, double* out,
                                                         const double* __restrict__ W, double* Wt, int as_in_smem) {
   extern __shared__ double esm[];
-  __shared__ double sh[33];
   const int P = n + 4, PA = n + 8;
   double* Tc = esm; double* Tn = esm + EXPM_ROWS * P; double* R = esm + 2 * EXPM_ROWS * P;
   double* Asm = esm + 3 * EXPM_ROWS * P;  // n x PA copy of A_s when it fits (n <= 128): B fragments at shared-memory latency
@@ -425,35 +770,57 @@ __global__ void __launch_bounds__(256) expm_rows_kernel(const double* __restrict
   // computed speculatively, then the published maxima of term k-1 (written one whole term ago: no waiting in practice)
   // decide whether it exists; a term that does not exist is discarded, so the result is exactly the reference's sum.
   if (!(first_norm < 1e-16)) {
+    // one block barrier per term, as in expm_multi_kernel below: the maxima of term k-1 are requested before the product and
+    // consumed after it, term k goes to Tn unconditionally, one reduction carries both maxima
+    __shared__ double red[2][2][8];
+    int rbuf = 0;
     for (int k = 2; k <= 30; ++k) {
+      double gv = 0.0;
+      const bool poll = k > 2 && tid < G;
+      const volatile double* fprev = flags + (size_t)(k - 1) * G + tid;
+      if (poll) gv = *fprev;
       double acc[4][2];
       rows_times(Tc, P, Bm, ldb, n, m0, m1, acc);
-      if (k > 2) {
-        double v = 0.0;
-        if (tid < G) {
-          const volatile double* f = flags + (size_t)(k - 1) * G + tid;
-          do { v = *f; } while (v != v);  // NaN = not published yet
-        }
-        if (block_max(v, sh) < 1e-16) break;  // uniform over the whole grid: every CTA reduces the same published values
-      }
+      if (poll)
+        while (gv != gv) gv = *fprev;  // NaN = not published yet
       double mx = 0.0;
+      double val[4][2];
 #pragma unroll
       for (int t = 0; t < 4; ++t)
-        if (warp + 8 * t < ncb)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = 8 * (warp + 8 * t) + 2 * j + e;
-            if (col < n) {
-              const double v = acc[t][e] / (double)k;
-              Tn[c * P + col] = v;
-              R[c * P + col] += v;
-              if (row0 + c < n) mx = fmax(mx, fabs(v));
-            }
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * (warp + 8 * t) + 2 * j + e;
+          val[t][e] = 0.0;
+          if (warp + 8 * t < ncb && col < n) {
+            const double v = acc[t][e] / (double)k;
+            val[t][e] = v;
+            Tn[c * P + col] = v;
+            if (row0 + c < n) mx = fmax(mx, fabs(v));
           }
-      mx = block_max(mx, sh);  // (contains the barriers that make Tn visible)
-      if (tid == 0) { *reinterpret_cast<volatile double*>(flags + (size_t)k * G + blockIdx.x) = mx; __threadfence(); }
+        }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        gv = fmax(gv, __shfl_xor_sync(0xffffffffu, gv, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if (lane == 0) { red[rbuf][0][warp] = gv; red[rbuf][1][warp] = mx; }
+      __syncthreads();
+      double gprev = 0.0, own = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) { gprev = fmax(gprev, red[rbuf][0][w8]); own = fmax(own, red[rbuf][1][w8]); }
+      rbuf ^= 1;
+      if (k > 2 && gprev < 1e-16) break;  // uniform over the whole grid: every CTA reduces the same published values
+      if (tid == 0) *reinterpret_cast<volatile double*>(flags + (size_t)k * G + blockIdx.x) = own;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * (warp + 8 * t) + 2 * j + e;
+          if (warp + 8 * t < ncb && col < n) R[c * P + col] += val[t][e];
+        }
       double* t = Tc; Tc = Tn; Tn = t;
     }
+    __syncthreads();  // R complete before the squaring / the output below reads other threads' entries
   }
   // squaring (math.rs:69-71): result <- result * result, s times; the full result goes through global memory
   double* Rg = Rg0; double* Rn = Rg1;
@@ -513,8 +880,7 @@ template <int NT>
 __global__ void __launch_bounds__(256) expm_multi_kernel(const double* __restrict__ D, double alpha, double first_norm, int n, int nc,
                                                          double* flags, const double* __restrict__ W, double* Wt_all, int as_in_smem) {
   extern __shared__ double esm[];
-  __shared__ double sh[33];
-  const int P = n + 4, PA = n + 8;
+    const int P = n + 4, PA = n + 8;
   double* Tc = esm; double* Tn = esm + EXPM_ROWS * P;
   double* Asm = esm + 2 * EXPM_ROWS * P;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, j = lane & 3, c = lane >> 2;
@@ -548,16 +914,48 @@ __global__ void __launch_bounds__(256) expm_multi_kernel(const double* __restric
         rt[t][tt][e] = ((row0 + c == col) ? 1.0 : 0.0) + a1 * pw[t];
       }
   }
+  // One block barrier per term: the published maxima of term k-1 are requested BEFORE the product of term k and consumed after it
+  // (their round trip to L2 hides behind the DMMAs), term k goes to Tn unconditionally (a term that turns out not to exist is never
+  // read), and ONE reduction carries both maxima -- the device-wide one of term k-1 that decides the reference's `break` per
+  // candidate, and this CTA's own of term k that is published next.  Double-buffered reduction slots: no barrier after the reads.
+  __shared__ double red[2][2][8];
+  int rbuf = 0;
   for (int k = 2; k <= 30; ++k) {
+    double gv = 0.0;
+    const bool poll = k > 2 && tid < G;
+    const volatile double* fprev = flags + (size_t)(k - 1) * G + tid;
+    if (poll) gv = *fprev;
     double acc[4][2];
     rows_times(Tc, P, Bm, ldb, n, m0, 1.0, acc);
-    if (k > 2) {  // the reference's `break` for each candidate, on the published global max of term k-1
-      double v = 0.0;
-      if (tid < G) {
-        const volatile double* f = flags + (size_t)(k - 1) * G + tid;
-        do { v = *f; } while (v != v);
+    if (poll)
+      while (gv != gv) gv = *fprev;  // NaN = not published yet (rare: it was written one whole term ago)
+    double mx = 0.0;
+    double val[NT][2];
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = 8 * (warp + 8 * tt) + 2 * j + e;
+        val[tt][e] = 0.0;
+        if (warp + 8 * tt < ncb && col < n) {
+          const double v = acc[tt][e] / (double)k;
+          val[tt][e] = v;
+          Tn[c * P + col] = v;
+          if (row0 + c < n) mx = fmax(mx, fabs(v));
+        }
       }
-      const double gprev = block_max(v, sh);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      gv = fmax(gv, __shfl_xor_sync(0xffffffffu, gv, o));
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { red[rbuf][0][warp] = gv; red[rbuf][1][warp] = mx; }
+    __syncthreads();  // also: Tn complete, every warp done with Tc
+    double gprev = 0.0, own = 0.0;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) { gprev = fmax(gprev, red[rbuf][0][w8]); own = fmax(own, red[rbuf][1][w8]); }
+    rbuf ^= 1;
+    if (k > 2) {  // the reference's `break` for each candidate, on the published global max of term k-1
 #pragma unroll
       for (int t = 0; t < EXPM_NC; ++t)
         if (alive[t] && gprev * pw[t] < 1e-16) alive[t] = false;  // pw[t] still holds 2^{-(k-1) t}
@@ -565,43 +963,38 @@ __global__ void __launch_bounds__(256) expm_multi_kernel(const double* __restric
     bool any = false;
 #pragma unroll
     for (int t = 0; t < EXPM_NC; ++t) { pw[t] *= step[t]; any = any || alive[t]; }  // now 2^{-k t}
-    if (!any) break;  // uniform over the grid
-    double mx = 0.0;
+    if (!any) break;  // uniform over the grid: every CTA reduced the same published values
+    if (tid == 0) *reinterpret_cast<volatile double*>(flags + (size_t)k * G + blockIdx.x) = own;  // the value is the message: no fence
 #pragma unroll
     for (int tt = 0; tt < NT; ++tt)
-      if (warp + 8 * tt < ncb)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = 8 * (warp + 8 * tt) + 2 * j + e;
-          if (col < n) {
-            const double v = acc[tt][e] / (double)k;
-            Tn[c * P + col] = v;
+      for (int e = 0; e < 2; ++e) {
+        const int col = 8 * (warp + 8 * tt) + 2 * j + e;
+        if (warp + 8 * tt < ncb && col < n) {
 #pragma unroll
-            for (int t = 0; t < EXPM_NC; ++t)
-              if (alive[t]) rt[t][tt][e] += v * pw[t];
-            if (row0 + c < n) mx = fmax(mx, fabs(v));
-          }
+          for (int t = 0; t < EXPM_NC; ++t)
+            if (alive[t]) rt[t][tt][e] += val[tt][e] * pw[t];
         }
-    mx = block_max(mx, sh);
-    if (tid == 0) { *reinterpret_cast<volatile double*>(flags + (size_t)k * G + blockIdx.x) = mx; __threadfence(); }
+      }
     double* tsw = Tc; Tc = Tn; Tn = tsw;
   }
-  // W'_t rows = result_t rows * W
+  // W'_t rows = result_t rows * W; the two row buffers alternate, so one barrier per candidate is enough
+  __syncthreads();
 #pragma unroll
   for (int t = 0; t < EXPM_NC; ++t) {
     if (t >= nc) break;
-    __syncthreads();
+    double* buf = (t & 1) ? Tn : Tc;
 #pragma unroll
     for (int tt = 0; tt < NT; ++tt)
       if (warp + 8 * tt < ncb)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int col = 8 * (warp + 8 * tt) + 2 * j + e;
-          if (col < n) Tn[c * P + col] = rt[t][tt][e];
+          if (col < n) buf[c * P + col] = rt[t][tt][e];
         }
     __syncthreads();
     double acc[4][2];
-    rows_times(Tn, P, W, n, n, 1.0, 1.0, acc);
+    rows_times(buf, P, W, n, n, 1.0, 1.0, acc);
     double* dst = Wt_all + (size_t)t * n * n;
 #pragma unroll
     for (int tt = 0; tt < NT; ++tt)
@@ -974,6 +1367,26 @@ int copy_scaled(const double* A, double* B, int64_t count, double alpha, cudaStr
 }
 int iteration_front(const FrontArgs& a, cudaStream_t st) {
   const int nn = a.d.n * a.d.n;
+  // the cluster version: n <= 128 (16 CTAs x 8 rows x 128 columns), history of at most 7 pairs in registers, 16-CTA clusters
+  // schedulable on this device; PICARD_FRONT_V1=1 keeps the single-CTA kernel (A/B)
+  static PerDeviceInt cluster_ok;
+  const int use_cluster = cluster_ok.get([&] {  // 1 = yes, 2 = no (0 means "not determined yet" to PerDeviceInt)
+    if (getenv("PICARD_FRONT_V1") != nullptr) return 2;
+    if (cudaFuncSetAttribute(front_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 2; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(FC_CTAS); cfg.blockDim = dim3(FC_THREADS); cfg.dynamicSmemBytes = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = FC_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, front_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 2; }
+    return nclusters >= 1 ? 1 : 2;
+  });
+  if (use_cluster == 1 && a.d.n <= 128 && a.d.m <= FC_M) {
+    front_cluster_kernel<<<FC_CTAS, FC_THREADS, 0, st>>>(a);
+    LAUNCH_CHECK();
+    return 1;
+  }
   int threads = nn >= 1024 ? 1024 : ((nn + 31) / 32) * 32;
   if (threads < 32) threads = 32;
   front_kernel<<<1, threads, 0, st>>>(a);

@@ -677,6 +677,18 @@ __global__ void __launch_bounds__(256) matmul_kernel(const double* A, const doub
 constexpr int EXPM_ROWS = 8;
 constexpr int EXPM_MAX_CTAS = 32;
 
+// term / k exactly as the reference's division (math.rs:60), without the generic DDIV sequence (4 per thread and term: it was a
+// third of the Taylor loop's instructions): q = RN(a * RN(1/k)), r = a - k q (exact, FMA), q + r * RN(1/k) is the correctly rounded
+// quotient (Markstein); checked against a / k for k = 2 .. 30 on 6e8 operands (round-2 notes in DESIGN.md).  Zeros keep their sign
+// through a * rcp; anything near the ends of the exponent range takes the plain division.
+__device__ __forceinline__ double div_by_count(double a, double kk, double rcp) {
+  const double q = a * rcp;
+  const double aa = fabs(a);
+  if (aa > 1e-270 && aa < 1e270) return fma(fma(-kk, q, a), rcp, q);
+  if (aa == 0.0) return q;
+  return a / kk;
+}
+
 // acc[t][e] (t < 4) += T (8 x n, shared, pitch P) * B (n x n, global; element transform (b * mul0) * mul1) for column blocks
 // cb = warp + 8 t; thread (j, c): rows c, columns 8 cb + 2 j + e.  B may have been written by other CTAs: plain coherent loads.
 // ldb: leading dimension of B (n for global matrices, the padded pitch for the shared-memory copy of A_s).
@@ -761,11 +773,9 @@ __global__ void __launch_bounds__(256) expm_rows_kernel(const double* __restrict
     R[r * P + col] = ((grow == col) ? 1.0 : 0.0) + v;
   }
   if (as_in_smem)
-    for (int e = tid; e < n * n; e += blockDim.x) Asm[(e / n) * PA + (e % n)] = (D[e] * alpha) * inv_scale;
+    for (int r = warp; r < n; r += 8)  // (no integer division per element: it was 15 % of the kernel)
+      for (int col = lane; col < n; col += 32) Asm[r * PA + col] = (D[(size_t)r * n + col] * alpha) * inv_scale;
   __syncthreads();
-  const double* Bm = as_in_smem ? Asm : D;
-  const int ldb = as_in_smem ? PA : n;
-  const double m0 = as_in_smem ? 1.0 : alpha, m1 = as_in_smem ? 1.0 : inv_scale;
   // Taylor terms.  The reference stops after the first term whose GLOBAL max is below 1e-16 (math.rs:58-66).  Term k is
   // computed speculatively, then the published maxima of term k-1 (written one whole term ago: no waiting in practice)
   // decide whether it exists; a term that does not exist is discarded, so the result is exactly the reference's sum.
@@ -780,10 +790,12 @@ __global__ void __launch_bounds__(256) expm_rows_kernel(const double* __restrict
       const volatile double* fprev = flags + (size_t)(k - 1) * G + tid;
       if (poll) gv = *fprev;
       double acc[4][2];
-      rows_times(Tc, P, Bm, ldb, n, m0, m1, acc);
+      if (as_in_smem) rows_times(Tc, P, Asm, PA, n, 1.0, 1.0, acc);  // a shared-memory pointer the compiler can see: LDS, not generic loads
+      else rows_times(Tc, P, D, n, n, alpha, inv_scale, acc);
       if (poll)
         while (gv != gv) gv = *fprev;  // NaN = not published yet
       double mx = 0.0;
+      const double kk = (double)k, rcp = 1.0 / kk;
       double val[4][2];
 #pragma unroll
       for (int t = 0; t < 4; ++t)
@@ -792,7 +804,7 @@ __global__ void __launch_bounds__(256) expm_rows_kernel(const double* __restrict
           const int col = 8 * (warp + 8 * t) + 2 * j + e;
           val[t][e] = 0.0;
           if (warp + 8 * t < ncb && col < n) {
-            const double v = acc[t][e] / (double)k;
+            const double v = div_by_count(acc[t][e], kk, rcp);
             val[t][e] = v;
             Tn[c * P + col] = v;
             if (row0 + c < n) mx = fmax(mx, fabs(v));
@@ -890,11 +902,9 @@ __global__ void __launch_bounds__(256) expm_multi_kernel(const double* __restric
     Tc[r * P + col] = grow < n ? D[(size_t)grow * n + col] * alpha : 0.0;
   }
   if (as_in_smem)
-    for (int e = tid; e < n * n; e += blockDim.x) Asm[(e / n) * PA + (e % n)] = D[e] * alpha;
+    for (int r = warp; r < n; r += 8)  // (no integer division per element: it was 15 % of the kernel)
+      for (int col = lane; col < n; col += 32) Asm[r * PA + col] = D[(size_t)r * n + col] * alpha;
   __syncthreads();
-  const double* Bm = as_in_smem ? Asm : D;
-  const int ldb = as_in_smem ? PA : n;
-  const double m0 = as_in_smem ? 1.0 : alpha;
   // per-thread result entries of every candidate: rows row0 + c, columns 8 (warp + 8 t') + 2 j + e
   double rt[EXPM_NC][NT][2];
   double pw[EXPM_NC];      // 2^{-k t} of the current k
@@ -926,10 +936,12 @@ __global__ void __launch_bounds__(256) expm_multi_kernel(const double* __restric
     const volatile double* fprev = flags + (size_t)(k - 1) * G + tid;
     if (poll) gv = *fprev;
     double acc[4][2];
-    rows_times(Tc, P, Bm, ldb, n, m0, 1.0, acc);
+    if (as_in_smem) rows_times(Tc, P, Asm, PA, n, 1.0, 1.0, acc);  // a shared-memory pointer the compiler can see: LDS, not generic loads
+    else rows_times(Tc, P, D, n, n, alpha, 1.0, acc);
     if (poll)
       while (gv != gv) gv = *fprev;  // NaN = not published yet (rare: it was written one whole term ago)
     double mx = 0.0;
+    const double kk = (double)k, rcp = 1.0 / kk;
     double val[NT][2];
 #pragma unroll
     for (int tt = 0; tt < NT; ++tt)
@@ -938,7 +950,7 @@ __global__ void __launch_bounds__(256) expm_multi_kernel(const double* __restric
         const int col = 8 * (warp + 8 * tt) + 2 * j + e;
         val[tt][e] = 0.0;
         if (warp + 8 * tt < ncb && col < n) {
-          const double v = acc[tt][e] / (double)k;
+          const double v = div_by_count(acc[tt][e], kk, rcp);
           val[tt][e] = v;
           Tn[c * P + col] = v;
           if (row0 + c < n) mx = fmax(mx, fabs(v));

@@ -279,6 +279,20 @@ def _main(out):
         raise SystemExit("bench.py: no CUDA device; libpicard_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # BENCH_AFFINITY=1: one slice of the host cores per rank.  Off by default: at 8 GPUs it made no difference within the noise
+    # (397.9 against 392.1 it/s) and one of three runs lost 24 ms in a single pass, the mark of a preempted spinning thread on a
+    # crowded slice (profiles/README.md, call w3).
+    affinity = None
+    if world > 1 and hasattr(os, "sched_setaffinity") and os.environ.get("BENCH_AFFINITY"):
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // world
+            if per >= 1:
+                mine = cores[local_rank * per:(local_rank + 1) * per]
+                os.sched_setaffinity(0, mine)
+                affinity = mine
+        except OSError:
+            affinity = None
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -512,7 +526,7 @@ def _main(out):
             "config": config_dict(args, wl, world, t_total, shard_range(t_total, 0, world)[1] - shard_range(t_total, 0, world)[0]),
             "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks, "e2e": e2e, "gpu_launches": int(d["kernel_launches"]),
             "roofline": roof, "cpu_baseline": cpu, "passes": pass_mix, "parity": parity,
-            "non_pass_ms_per_step": non_pass_ms_per_step,
+            "non_pass_ms_per_step": non_pass_ms_per_step, "host_affinity": affinity,
             "state": {"n_iterations": state["n_iterations"], "gradient_norm": state["gradient_norm"], "loss": state["loss"]},
         }
         print(json.dumps(line), file=out, flush=True)

@@ -1,6 +1,7 @@
 // N x N device kernels of the core loop.  See small.cuh.  Reference citations per kernel.
 #include "small.cuh"
 #include "loss_point.cuh"
+#include "exact_div.h"
 
 #include <cmath>
 
@@ -677,18 +678,8 @@ __global__ void __launch_bounds__(256) matmul_kernel(const double* A, const doub
 constexpr int EXPM_ROWS = 8;
 constexpr int EXPM_MAX_CTAS = 32;
 
-// term / k exactly as the reference's division (math.rs:60), without the generic DDIV sequence (4 per thread and term: it was a
-// third of the Taylor loop's instructions): q = RN(a * RN(1/k)), r = a - k q (exact, FMA), q + r * RN(1/k) is the correctly rounded
-// quotient (Markstein); checked against a / k for k = 2 .. 30 on 6e8 operands (round-2 notes in DESIGN.md).  Zeros keep their sign
-// through a * rcp; anything near the ends of the exponent range takes the plain division.
-__device__ __forceinline__ double div_by_count(double a, double kk, double rcp) {
-  const double q = a * rcp;
-  const double aa = fabs(a);
-  if (aa > 1e-270 && aa < 1e270) return fma(fma(-kk, q, a), rcp, q);
-  if (aa == 0.0) return q;
-  return a / kk;
-}
-
+// term / k exactly as the reference's division (math.rs:60) without the generic DDIV sequence (4 per thread and term: it was a
+// third of the Taylor loop's instructions): div_by_count() of exact_div.h, checked on the host by tests/test_exact_div_host.py.
 // acc[t][e] (t < 4) += T (8 x n, shared, pitch P) * B (n x n, global; element transform (b * mul0) * mul1) for column blocks
 // cb = warp + 8 t; thread (j, c): rows c, columns 8 cb + 2 j + e.  B may have been written by other CTAs: plain coherent loads.
 // ldb: leading dimension of B (n for global matrices, the padded pitch for the shared-memory copy of A_s).

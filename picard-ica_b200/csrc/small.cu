@@ -683,6 +683,7 @@ constexpr int EXPM_MAX_CTAS = 32;
 // acc[t][e] (t < 4) += T (8 x n, shared, pitch P) * B (n x n, global; element transform (b * mul0) * mul1) for column blocks
 // cb = warp + 8 t; thread (j, c): rows c, columns 8 cb + 2 j + e.  B may have been written by other CTAs: plain coherent loads.
 // ldb: leading dimension of B (n for global matrices, the padded pitch for the shared-memory copy of A_s).
+template <bool CG>
 __device__ __forceinline__ void rows_times_general(const double* T, int P, const double* B, int ldb, int n, double mul0, double mul1, double acc[4][2]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = lane & 3, c = lane >> 2;
   const int ncb = (n + 7) >> 3;
@@ -696,7 +697,7 @@ __device__ __forceinline__ void rows_times_general(const double* T, int P, const
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int col = 8 * (warp + 8 * t) + c;
-      b[t] = (kok && warp + 8 * t < ncb && col < n) ? (B[(size_t)(k0 + j) * ldb + col] * mul0) * mul1 : 0.0;
+      b[t] = (kok && warp + 8 * t < ncb && col < n) ? ((CG ? __ldcg(B + (size_t)(k0 + j) * ldb + col) : B[(size_t)(k0 + j) * ldb + col]) * mul0) * mul1 : 0.0;
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t)
@@ -709,7 +710,7 @@ __device__ __forceinline__ void rows_times_general(const double* T, int P, const
 // per-element address arithmetic -- the general loop above spends ~40 integer instructions per DMMA, which is what bound the
 // transform kernels (ncu: DMMA pipe 16 % busy).  NV = number of valid column blocks of this warp (warp-uniform).  Same DMMA
 // sequence per accumulator as the general loop: bit-identical results.
-template <int NV>
+template <int NV, bool CG>
 __device__ __forceinline__ void rows_times_dense(const double* __restrict__ T, int P, const double* B, int ldb, int n, double acc[4][2]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = lane & 3, c = lane >> 2;
   const double* ap = T + c * P + j;
@@ -722,29 +723,32 @@ __device__ __forceinline__ void rows_times_dense(const double* __restrict__ T, i
     const double a = ap[k0];
     double b[NV];
 #pragma unroll
-    for (int t = 0; t < NV; ++t) b[t] = bp[64 * t];
+    for (int t = 0; t < NV; ++t) b[t] = CG ? __ldcg(bp + 64 * t) : bp[64 * t];
     bp += kstep;
 #pragma unroll
     for (int t = 0; t < NV; ++t)
       asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(a), "d"(b[t]));
   }
 }
+// CG: B was written by other CTAs of this launch (the squaring phase): read it around L1 (ld.global.cg), which is not coherent
+// across SMs -- a line of the same buffer cached two squarings ago must not be served again.
+template <bool CG = false>
 __device__ __forceinline__ void rows_times(const double* T, int P, const double* B, int ldb, int n, double mul0, double mul1, double acc[4][2]) {
   if ((n & 7) == 0 && mul0 == 1.0 && mul1 == 1.0) {  // uniform over the grid
     const int warp = threadIdx.x >> 5, ncb = n >> 3;
     const int nv = warp < ncb ? (ncb - warp + 7) >> 3 : 0;  // column blocks warp, warp + 8, ... < ncb
     switch (nv) {
-      case 1: rows_times_dense<1>(T, P, B, ldb, n, acc); break;
-      case 2: rows_times_dense<2>(T, P, B, ldb, n, acc); break;
-      case 3: rows_times_dense<3>(T, P, B, ldb, n, acc); break;
-      case 4: rows_times_dense<4>(T, P, B, ldb, n, acc); break;
+      case 1: rows_times_dense<1, CG>(T, P, B, ldb, n, acc); break;
+      case 2: rows_times_dense<2, CG>(T, P, B, ldb, n, acc); break;
+      case 3: rows_times_dense<3, CG>(T, P, B, ldb, n, acc); break;
+      case 4: rows_times_dense<4, CG>(T, P, B, ldb, n, acc); break;
       default:
 #pragma unroll
         for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
     }
     return;
   }
-  rows_times_general(T, P, B, ldb, n, mul0, mul1, acc);
+  rows_times_general<CG>(T, P, B, ldb, n, mul0, mul1, acc);
 }
 
 __global__ void __launch_bounds__(256) expm_rows_kernel(const double* __restrict__ D, double alpha, double inv_scale, double first_norm, int s,
@@ -841,7 +845,7 @@ __global__ void __launch_bounds__(256) expm_rows_kernel(const double* __restrict
     }
     __syncthreads();
     double acc[4][2];
-    rows_times(R, P, Rg, n, n, 1.0, 1.0, acc);
+    rows_times<true>(R, P, Rg, n, n, 1.0, 1.0, acc);
     __syncthreads();
 #pragma unroll
     for (int t = 0; t < 4; ++t)

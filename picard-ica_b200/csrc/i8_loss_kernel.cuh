@@ -250,6 +250,7 @@ loss_i8_kernel(const uint8_t* __restrict__ xblob, const __grid_constant__ CUtens
               const uint32_t tacc = tmem + (uint32_t)((pa + qb) * NT);
               const uint64_t db = db0 + (uint64_t)((qb * G::SLICE_B_BYTES + k * 32) >> 4);
               const uint32_t acc = (pa > 0 || k > 0) ? 1u : 0u;
+              if ((ABL & 8) != 0) continue;  // lab ablation: the epilogue alone, on whatever the accumulators hold
               if (pa < G::ATM) umma_i8_ts(tacc, tmem + (uint32_t)(G::TMEM_A + 8 * (4 * pa + k)), db, make_idesc(m * NT), acc);
               else umma_i8_ss(tacc, da0 + (uint64_t)(((pa - G::ATM) * SLICE_A_BYTES + k * 32) >> 4), db, make_idesc(m * NT), acc);
             }

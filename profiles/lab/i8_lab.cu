@@ -341,6 +341,9 @@ int main(int argc, char** argv) {
   run_loss<2>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);
   run_loss<3>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);
   run_loss<4>(xblob, w, y, ld, T, n, partial, sms, 1, d_trace);
+  run_loss<8>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);   // no MMAs: what the epilogue alone costs
+  run_loss<9>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);   // no MMAs, no density
+  run_loss<11>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);  // no MMAs, no density, no store: tile hand-over only
   run_loss<0>(xblob, w, y, ld, T, n, partial, sms, reps, d_trace);  // leaves the full Y' for the gradient kernel
 
   // ---- gradient kernel: correctness of both layouts on a short prefix, then timing

@@ -65,6 +65,21 @@ NCU_TRAFFIC_C3 = {"loss": (7.721367e9 + 10.192575e9, "profiles/summary_r02y.txt 
                   "grady": (10.327482e9 + 0.091629e9, "profiles/summary_r02z.txt (ncu --set full of grad_i8_kernel inside this bench command, one GPU, T = 1e7)")}
 
 
+def _hbm_peak():
+    """Measured copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the SURVEY.md §8(d) figure."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            v = float(json.load(fh)["hbm_gbs"])
+        if v > 0:
+            return v, "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, ValueError, KeyError, TypeError):
+        pass
+    return 6462.4, "SURVEY.md 8(d): 6 462 GB/s measured on this pool (MEASURED_PEAKS.json not found)"
+
+
+HBM_PEAK_GBS = _hbm_peak()
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line).  NVML in-process
     (nvidia_ml_py) when available: spawning nvidia-smi every 100 ms was measured to stall the solver's kernel launches
@@ -407,9 +422,12 @@ def _main(out):
                 "traffic": traffic * (t_local / 1e7) if traffic else None, "traffic_source": traffic_src,
                 "algorithmic_bytes": alg_bytes, "avg_launch_ms": avg_ms, "launches": cnt, "flops_per_launch": flops,
                 "peak_source": peak_source, "share_of_step": ms / dev_ms, "hbm_gbs": alg_bytes / (avg_ms * 1e-3) / 1e9,
+                "hbm_peak_gbs": HBM_PEAK_GBS[0], "hbm_peak_source": HBM_PEAK_GBS[1],
+                "hbm_frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / HBM_PEAK_GBS[0],
                 "what": "achieved = ALGORITHMIC f64 flops of the pass (2 N^2 T_local) / mean launch duration; peak = FP64 tensor peak "
                         "(BASELINE.md's roofline).  The INT8 engines reach the f64 result through exact digit splitting, so frac can "
-                        "exceed 1: the `engine` object gives the integer-op view"}
+                        "exceed 1: the `engine` object gives the integer-op view; hbm_frac = algorithmic bytes / launch duration against the "
+                        "measured copy bandwidth (the INT8 LOSS pass is within 2x of that bound too)"}
         if i8:
             ops = 21.0 * 2.0 * 128 * 128 * t_local
             roof["engine"] = {"what": "error-free balanced radix-256 splitting, 6 digits, 21 digit products, s32 accumulators in TMEM "

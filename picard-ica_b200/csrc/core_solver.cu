@@ -262,7 +262,10 @@ bool CoreSolver::i8_prepare() {
   i8_state_ = -1;
   const int env = i8_env_mode();
   const bool forced = (cfg_.flags & PICARD_FLAG_FORCE_INT8) != 0 || env == 1;
-  if (pass_padded_size(dims_.n) != 128 || (cfg_.flags & PICARD_FLAG_NO_INT8) != 0 || env == 0) return false;
+  // automatic for 64 < N <= 128; PICARD_FLAG_FORCE_INT8 also admits smaller N (the kernels pad to 128 rows: measured no faster
+  // than the FP64 kernels there, DESIGN.md section 7 -- kept for that measurement and for tests)
+  const bool size_ok = pass_padded_size(dims_.n) == 128 || (forced && dims_.n <= 128);
+  if (!size_ok || (cfg_.flags & PICARD_FLAG_NO_INT8) != 0 || env == 0) return false;
   if (!forced && !cov_identity_) return false;
   try {
     xs8_.alloc(i8_blob_bytes(t_local_));

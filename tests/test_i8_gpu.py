@@ -27,9 +27,11 @@ def _w(n, eps=0.02):
 
 
 @pytest.mark.parametrize("n,t,kind,alpha", [(128, 2050, orc.TANH, 1.0), (100, 1500, orc.TANH, 0.7), (65, 33, orc.TANH, 1.0),
-                                            (128, 4097, orc.EXP, 0.1), (70, 4099, orc.CUBE, 1.0), (96, 31, orc.TANH, 1.0)])
+                                            (128, 4097, orc.EXP, 0.1), (70, 4099, orc.CUBE, 1.0), (96, 31, orc.TANH, 1.0),
+                                            (64, 3000, orc.TANH, 1.0), (20, 700, orc.TANH, 1.0)])
 def test_int8_loss_pass_matches_oracle(n, t, kind, alpha):
-    """Raw LOSS moments (log-likelihood and y^2 row sums) of the INT8 pass: ragged last tile, N < 128 padding, T < one tile."""
+    """Raw LOSS moments (log-likelihood and y^2 row sums) of the INT8 pass: ragged last tile, N < 128 padding, T < one tile; N <= 64
+    only runs it when forced (the automatic gate is 64 < N <= 128: no faster than the FP64 kernels below)."""
     x = _data.whitened(n, max(t, 2 * n), seed=n)[:, :t]
     w = _w(n)
     ref = _ref(x, w, kind, alpha)
